@@ -1,0 +1,56 @@
+"""Pins oracle/rangelib_oracle.c against the UNMODIFIED reference compiled into
+oracle/_ref/libref_strict.so, on fresh seeded inputs (not the committed vectors).
+Skipped when the reference library has not been built (it is built from /root/reference by
+oracle/Makefile in the authoring container and travels to the GPU box as a binary)."""
+import numpy as np
+import pytest
+
+from oracle import port, ref
+from range_libc_b200 import workloads as wl
+from helpers import assert_bit_equal
+
+pytestmark = pytest.mark.skipif(not ref.available("strict"), reason="oracle/_ref not built")
+
+
+@pytest.mark.parametrize("name", ["basement_hallways_10cm", "basement_fixed_rectangle", "small.map"])
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_fresh_queries_bit_equal(name, kind):
+    occ = wl.load_map(name)
+    W, H = occ.shape
+    q = wl.random_queries(W, H, 20000, seed=1000 + kind)
+    rmap = ref.RefMap(occ=occ)
+    r = ref.RefMethod(kind, rmap, 500.0, 108)
+    o = port.Oracle(kind, occ, 500.0, 108)
+    assert_bit_equal(o.calc_range_many(q), r.calc_range_many(q), "kind %d" % kind)
+    if kind == 1:
+        assert_bit_equal(o.dt(), r.dt(), "dt")
+    if kind >= 2:
+        for a, b in zip(o.cddt_table(), r.cddt_table(108)):
+            assert_bit_equal(a, b, "cddt table")
+
+
+def test_edge_map_equal():
+    occ = wl.load_map("basement_hallways_10cm")
+    assert (port.edge_map(occ) == ref.RefMap(occ=occ).edge()).all()
+
+
+def test_other_theta_discretizations():
+    occ = wl.load_map("basement_hallways_10cm")
+    q = wl.random_queries(600, 600, 5000, seed=77)
+    for td in (7, 16, 360):
+        r = ref.RefMethod(ref.PCDDT, ref.RefMap(occ=occ), 300.0, td)
+        o = port.Oracle(port.PCDDT, occ, 300.0, td)
+        assert_bit_equal(o.calc_range_many(q), r.calc_range_many(q), "td %d" % td)
+        for a, b in zip(o.cddt_table(), r.cddt_table(td)):
+            assert_bit_equal(a, b, "table td %d" % td)
+
+
+def test_multithreaded_slicing_is_identical():
+    occ = wl.load_map("basement_hallways_10cm")
+    q = wl.random_queries(600, 600, 5000, seed=78)
+    a = port.Oracle(1, occ, 500.0, threads=1).numpy_calc_range(q)
+    b = port.Oracle(1, occ, 500.0, threads=4).numpy_calc_range(q)
+    assert_bit_equal(a, b)
+    rmap = ref.RefMap(occ=occ)
+    c = ref.RefMethod(1, rmap, 500.0, threads=4).numpy_calc_range(q)
+    assert_bit_equal(a, c)
