@@ -1,0 +1,134 @@
+/* rangelib_b200 -- C ABI of the B200-native batched 2-D ray casting path.
+ *
+ * This is the drop-in boundary: the entry points below are exactly what the reference's
+ * Cython binding (range_libc, /root/reference/pywrapper/RangeLibc.pyx) needs from a backend
+ * for its RangeMethod classes.  Each declaration cites the reference interface it replaces.
+ * Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative RL_E_* code on failure;
+ *    rl_last_error() returns a thread-local message for the last failure.  (The reference
+ *    returns void and prints / throws std::string / is UB; see INTEGRATION.md.)
+ *  - data pointers (ins, angles, obs, ranges, outs, weights) may be HOST or DEVICE memory;
+ *    the library detects which with cudaPointerGetAttributes.
+ *      host   : inputs are staged to the device, the call returns after the results are back
+ *               in the caller's buffer (same blocking semantics as the reference);
+ *      device : the kernels run in place on the handle's stream and the call returns without
+ *               synchronising (rl_method_synchronize() or the caller's own stream sync).
+ *    All data pointers of one call must live on the same side.
+ *  - buffers are caller-owned and borrowed for the duration of the call, never retained
+ *    (RangeLibc.pyx:208-225 passes numpy buffers the same way).
+ *  - handles are thread-compatible: use one rl_method per host thread / stream.
+ *  - occupancy grids are x-major bytes: occ[x*H + y] != 0  <=>  OMap::grid[x][y]
+ *    (/root/reference/includes/RangeLib.h:126).
+ */
+#ifndef RANGELIB_B200_H
+#define RANGELIB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rl_map rl_map;
+typedef struct rl_method rl_method;
+
+/* range method kinds (RangeLib.h: BresenhamsLine :691, RayMarching :922 / RayMarchingGPU :774,
+ * CDDTCast :971; PCDDT = CDDTCast + prune() :1176) */
+enum { RL_BL = 0, RL_RM = 1, RL_CDDT = 2, RL_PCDDT = 3 };
+
+enum {
+  RL_OK = 0,
+  RL_E_INVALID = -1,   /* bad argument */
+  RL_E_CUDA = -2,      /* CUDA runtime failure (message has the cudaError string) */
+  RL_E_NO_DEVICE = -3, /* no usable sm_100 device: the library has NO CPU fallback */
+  RL_E_STATE = -4,     /* call not valid for this handle (e.g. prune on RM, no sensor model) */
+  RL_E_MIXED = -5      /* host and device pointers mixed in one call */
+};
+
+const char* rl_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+uint64_t rl_stat_kernel_launches(void);
+
+/* ---- OMap (RangeLib.h:121-322; Python PyOMap RangeLibc.pyx:130-198) ---------------------- */
+/* replaces OMap(w,h)+grid fill (RangeLibc.pyx:138-145); copies occ */
+int rl_map_create(const uint8_t* occ_xmajor, int width, int height, rl_map** out);
+/* replaces the world_* field stores at RangeLibc.pyx:160-166 / 174-180; defaults 1,0,0,0,0,1 */
+int rl_map_set_world(rl_map* map, float scale, float angle, float origin_x, float origin_y, float sin_angle,
+                     float cos_angle);
+int rl_map_width(const rl_map* map);
+int rl_map_height(const rl_map* map);
+/* OMap::get / isOccupied (RangeLib.h:203-210): 1 occupied, 0 free or out of bounds */
+int rl_map_is_occupied(const rl_map* map, int x, int y);
+/* copy the grid out (x-major bytes) */
+int rl_map_get(const rl_map* map, uint8_t* out_xmajor);
+/* extension for dynamic maps (BASELINE config 4): overwrite the w*h patch at (x0,y0);
+ * patch is x-major patch[(x-x0)*h + (y-y0)].  Host side only; see rl_method_update_map. */
+int rl_map_update(rl_map* map, const uint8_t* patch_xmajor, int x0, int y0, int w, int h);
+void rl_map_destroy(rl_map* map);
+
+/* ---- RangeMethod construction ------------------------------------------------------------ */
+/* replaces BresenhamsLine(OMap,mr) :694, RayMarching(OMap,mr) :925, RayMarchingGPU(OMap,mr) :777,
+ * CDDTCast(OMap,mr,td) :974 (+ prune for RL_PCDDT).  The map (and its world parameters) is
+ * copied, like the reference's by-value OMap.  All acceleration structures (distance
+ * transform, CDDT tables) are BUILT ON THE DEVICE and stay resident there.
+ * device < 0 selects the current CUDA device. */
+int rl_method_create(int kind, const rl_map* map, float max_range, unsigned theta_discretization, int device,
+                     rl_method** out);
+void rl_method_destroy(rl_method* m);
+/* CDDTCast::prune(max_range) RangeLib.h:1176 (PyCDDTCast.prune RangeLibc.pyx:263-267) */
+int rl_method_prune(rl_method* m, float max_range);
+/* run this handle's work on the given cudaStream_t (NULL = the handle's own stream) */
+int rl_method_set_stream(rl_method* m, void* cuda_stream);
+int rl_method_synchronize(rl_method* m);
+/* dynamic maps: apply an occupancy patch on the device and refresh the structures that depend
+ * on it (BL: bit grid only; RM: distance transform rebuilt; CDDT: table rebuilt).
+ * patch may be host or device memory. */
+int rl_method_update_map(rl_method* m, const uint8_t* patch_xmajor, int x0, int y0, int w, int h);
+/* bytes of device memory held by the acceleration structure (RangeMethod::memory()) */
+int64_t rl_method_memory(const rl_method* m);
+
+/* ---- queries -------------------------------------------------------------------------------- */
+/* RangeMethod::calc_range(x,y,heading) RangeLib.h:418 -- one ray, grid coordinates.  Works for
+ * every kind including RM-on-GPU (the reference's RayMarchingGPU::calc_range only prints,
+ * RangeLib.h:800-807). */
+int rl_calc_range(rl_method* m, float x, float y, float heading, float* out);
+/* RayMarchingGPU::calc_range_many(ins,outs,n) RangeLib.h:819-831: n rays (x,y,theta) AoS in GRID
+ * coordinates, no world conversion. */
+int rl_calc_range_many(rl_method* m, const float* ins, float* outs, int num_casts);
+/* RangeMethod::numpy_calc_range(ins,outs,n) RangeLib.h:439-480 (Python calc_range_many):
+ * WORLD coordinates, ROS conversion incl. the x/y swap, result scaled by world_scale. */
+int rl_numpy_calc_range(rl_method* m, const float* ins, float* outs, int num_casts);
+/* RangeMethod::numpy_calc_range_angles RangeLib.h:482-520 (Python calc_range_repeat_angles):
+ * outs[i*num_angles + a] for particle i and angle a. */
+int rl_numpy_calc_range_angles(rl_method* m, const float* ins, const float* angles, float* outs, int num_particles,
+                               int num_angles);
+/* RangeMethod::set_sensor_model(table,k) RangeLib.h:523-532.  REPLACES the table (the reference
+ * appends rows when called twice; calling once is identical). table is HOST or DEVICE, k*k doubles. */
+int rl_set_sensor_model(rl_method* m, const double* table, int table_width);
+/* RangeMethod::eval_sensor_model(obs,ranges,outs,rays_per_particle,particles) RangeLib.h:533-555 */
+int rl_eval_sensor_model(rl_method* m, const float* obs, const float* ranges, double* outs, int rays_per_particle,
+                         int particles);
+/* RangeMethod::calc_range_repeat_angles_eval_sensor_model RangeLib.h:558-612 -- fused: ranges
+ * never leave the SM. */
+int rl_calc_range_repeat_angles_eval_sensor_model(rl_method* m, const float* ins, const float* angles,
+                                                  const float* obs, double* weights, int num_particles,
+                                                  int num_angles);
+
+/* ---- table-level access for parity tests ---------------------------------------------------- */
+/* distance transform, x-major out[x*H+y] (DistanceTransform::grid RangeLib.h:328); RL_RM only. out: HOST */
+int rl_debug_get_dt(rl_method* m, float* out);
+/* CDDT tables (CDDTCast::compressed_lut / lut_translations RangeLib.h:1746-1748) in CSR form.
+ * widths/translations: theta_discretization entries each (may be NULL); returns the total
+ * number of bins in *n_bins and of zero points in *n_values. */
+int rl_debug_cddt_dims(rl_method* m, int64_t* n_bins, int64_t* n_values, int* widths, float* translations);
+/* offsets: n_bins+1 int64, values: n_values floats; HOST buffers */
+int rl_debug_cddt_dump(rl_method* m, int64_t* offsets, float* values);
+/* device trig used by BL/RM (restated glibc sinf/cosf); HOST buffers; for tests */
+int rl_debug_sincosf(const float* x, float* s, float* c, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANGELIB_B200_H */

@@ -1,0 +1,255 @@
+"""Python mirror of the reference's ``range_libc`` classes on top of the C ABI (cabi.py)."""
+import ctypes as C
+
+import numpy as np
+
+from . import cabi
+from .cabi import check, lib
+
+
+def kernel_launches():
+    return int(lib().rl_stat_kernel_launches())
+
+
+def _is_torch(a):
+    return hasattr(a, "data_ptr") and hasattr(a, "is_cuda")
+
+
+def _buf(a, dtype, ndim, name):
+    """Pointer + shape of a C-contiguous array of the exact dtype/ndim, numpy or torch.  Mirrors the
+    typed-memoryview checks of the reference's Cython signatures (ValueError on mismatch)."""
+    if _is_torch(a):
+        import torch
+        want = {np.float32: torch.float32, np.float64: torch.float64, np.uint8: torch.uint8}[dtype]
+        if a.dtype != want:
+            raise ValueError("%s: expected dtype %s, got %s" % (name, want, a.dtype))
+        if a.dim() != ndim:
+            raise ValueError("%s: expected %d dimensions, got %d" % (name, ndim, a.dim()))
+        if not a.is_contiguous():
+            raise ValueError("%s: tensor is not contiguous" % name)
+        return C.c_void_p(a.data_ptr()), tuple(a.shape)
+    if not isinstance(a, np.ndarray):
+        raise ValueError("%s: expected a numpy array or torch tensor" % name)
+    if a.dtype != dtype:
+        raise ValueError("%s: Buffer dtype mismatch, expected %s but got %s" % (name, np.dtype(dtype), a.dtype))
+    if a.ndim != ndim:
+        raise ValueError("%s: Buffer has wrong number of dimensions (expected %d, got %d)" % (name, ndim, a.ndim))
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("%s: ndarray is not C-contiguous" % name)
+    return C.c_void_p(a.ctypes.data), a.shape
+
+
+class PyOMap:
+    """PyOMap(np.ndarray bool[H, W]) | PyOMap(width, height) | PyOMap(OccupancyGrid-like msg)
+    (RangeLibc.pyx:130-198).  PNG paths are not decoded here: PNG ingest is outside the hot path
+    (SURVEY.md section 8f); load the image with any decoder and pass the boolean array.
+
+    Grid convention of the reference: grid[x][y] with x the image column and y the image row, so a
+    numpy image ``arr[row, col]`` maps to grid[col][row]."""
+
+    def __init__(self, arg1, arg2=None):
+        self._h = C.c_void_p()
+        world = None
+        if isinstance(arg1, (int, np.integer)) and isinstance(arg2, (int, np.integer)):
+            occ = np.zeros((int(arg1), int(arg2)), np.uint8)
+        elif isinstance(arg1, np.ndarray):
+            if arg1.ndim != 2:
+                raise ValueError("occupancy array must be 2-D")
+            occ = np.ascontiguousarray(arg1.T != 0, dtype=np.uint8)  # [W, H] x-major
+        elif hasattr(arg1, "info") and hasattr(arg1, "data"):
+            # ROS nav_msgs/OccupancyGrid: 0 permissible, -1 unmapped, 100 blocked (pyx:146-167).
+            # The reference builds OMap(height, width) and fills grid[x][y] for x in range(height),
+            # y in range(width) from data.reshape(height, width)[x, y] > 10.
+            info = arg1.info
+            arr = np.asarray(arg1.data).reshape((info.height, info.width))
+            occ = np.ascontiguousarray(arr > 10, dtype=np.uint8)  # grid[x=row][y=col]
+            q = info.origin.orientation
+            yaw = np.arctan2(2.0 * (q.w * q.z + q.x * q.y), 1.0 - 2.0 * (q.y * q.y + q.z * q.z))
+            angle = -1.0 * yaw
+            world = (info.resolution, angle, info.origin.position.x, info.origin.position.y, np.sin(angle),
+                     np.cos(angle))
+        else:
+            raise ValueError("Failed to construct PyOMap, check argument types "
+                             "(PNG decoding is not part of this backend; pass a boolean array).")
+        self._w, self._hgt = occ.shape
+        check(lib().rl_map_create(C.c_void_p(occ.ctypes.data), occ.shape[0], occ.shape[1], C.byref(self._h)))
+        if world is not None:
+            self.set_world(*world)
+
+    def set_world(self, scale=1.0, angle=0.0, origin_x=0.0, origin_y=0.0, sin_angle=0.0, cos_angle=1.0):
+        check(lib().rl_map_set_world(self._h, scale, angle, origin_x, origin_y, sin_angle, cos_angle))
+
+    def isOccupied(self, x, y):
+        return bool(lib().rl_map_is_occupied(self._h, int(x), int(y)))
+
+    def error(self):
+        return False
+
+    def width(self):
+        return self._w
+
+    def height(self):
+        return self._hgt
+
+    def grid(self):
+        out = np.empty((self._w, self._hgt), np.uint8)
+        check(lib().rl_map_get(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def update(self, patch_xmajor, x0, y0):
+        """Dynamic maps: overwrite a [w, h] x-major patch of the HOST map (see RangeMethod.update_map)."""
+        p = np.ascontiguousarray(patch_xmajor, dtype=np.uint8)
+        check(lib().rl_map_update(self._h, C.c_void_p(p.ctypes.data), int(x0), int(y0), p.shape[0], p.shape[1]))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().rl_map_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class _RangeMethod:
+    _kind = None
+
+    def __init__(self, Map, max_range, theta_disc=0, device=-1):
+        self._h = C.c_void_p()
+        self.max_range = float(max_range)
+        self._map = Map
+        check(lib().rl_method_create(self._kind, Map._h, float(max_range), int(theta_disc), int(device),
+                                     C.byref(self._h)))
+
+    # -- reference API ---------------------------------------------------------------------
+    def calc_range(self, x, y, heading):
+        out = C.c_float()
+        check(lib().rl_calc_range(self._h, float(x), float(y), float(heading), C.byref(out)))
+        return out.value
+
+    def calc_range_many(self, ins, outs):
+        """ins f32[N,3] WORLD poses, outs f32[N]; N is taken from outs (RangeLibc.pyx:208-209)."""
+        pi, si = _buf(ins, np.float32, 2, "ins")
+        po, so = _buf(outs, np.float32, 1, "outs")
+        if si[1] != 3 or si[0] < so[0]:
+            raise ValueError("ins must be [N,3] with N >= len(outs)")
+        check(lib().rl_numpy_calc_range(self._h, pi, po, so[0]))
+
+    def calc_range_many_grid(self, ins, outs):
+        """RayMarchingGPU::calc_range_many (RangeLib.h:819-831): GRID coordinates, no conversion."""
+        pi, si = _buf(ins, np.float32, 2, "ins")
+        po, so = _buf(outs, np.float32, 1, "outs")
+        if si[1] != 3 or si[0] < so[0]:
+            raise ValueError("ins must be [N,3] with N >= len(outs)")
+        check(lib().rl_calc_range_many(self._h, pi, po, so[0]))
+
+    def calc_range_repeat_angles(self, ins, angles, outs):
+        pi, si = _buf(ins, np.float32, 2, "ins")
+        pa, sa = _buf(angles, np.float32, 1, "angles")
+        po, so = _buf(outs, np.float32, 1, "outs")
+        if si[1] != 3 or so[0] < si[0] * sa[0]:
+            raise ValueError("outs must hold N*M floats")
+        check(lib().rl_numpy_calc_range_angles(self._h, pi, pa, po, si[0], sa[0]))
+
+    def calc_range_repeat_angles_eval_sensor_model(self, ins, angles, obs, weights):
+        pi, si = _buf(ins, np.float32, 2, "ins")
+        pa, sa = _buf(angles, np.float32, 1, "angles")
+        pb, sb = _buf(obs, np.float32, 1, "obs")
+        pw, sw = _buf(weights, np.float64, 1, "weights")
+        if si[1] != 3 or sb[0] < sa[0] or sw[0] < si[0]:
+            raise ValueError("shape mismatch")
+        check(lib().rl_calc_range_repeat_angles_eval_sensor_model(self._h, pi, pa, pb, pw, si[0], sa[0]))
+
+    def eval_sensor_model(self, observation, ranges, outs, num_rays, num_particles):
+        pb, sb = _buf(observation, np.float32, 1, "observation")
+        pr, sr = _buf(ranges, np.float32, 1, "ranges")
+        po, so = _buf(outs, np.float64, 1, "outs")
+        if sb[0] < num_rays or sr[0] < num_rays * num_particles or so[0] < num_particles:
+            raise ValueError("shape mismatch")
+        check(lib().rl_eval_sensor_model(self._h, pb, pr, po, int(num_rays), int(num_particles)))
+
+    def set_sensor_model(self, table):
+        pt, st = _buf(table, np.float64, 2, "table")
+        if st[0] != st[1]:
+            print("Sensor model must have equal matrix dimensions, failing!")  # RangeLibc.pyx:222-224
+            return
+        check(lib().rl_set_sensor_model(self._h, pt, st[0]))
+
+    def saveTrace(self, path):
+        print("WARNING: trace map not generated, must compile with trace support enabled.")  # RangeLib.h:430
+
+    # -- extensions ------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        check(lib().rl_method_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(lib().rl_method_synchronize(self._h))
+
+    def update_map(self, patch_xmajor, x0, y0):
+        """Dynamic maps: apply a [w, h] x-major uint8 patch on the device and refresh the structures."""
+        if _is_torch(patch_xmajor):
+            pp, sp = _buf(patch_xmajor, np.uint8, 2, "patch")
+        else:
+            patch_xmajor = np.ascontiguousarray(patch_xmajor, dtype=np.uint8)
+            pp, sp = _buf(patch_xmajor, np.uint8, 2, "patch")
+        check(lib().rl_method_update_map(self._h, pp, int(x0), int(y0), sp[0], sp[1]))
+
+    def memory(self):
+        return int(lib().rl_method_memory(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().rl_method_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class PyBresenhamsLine(_RangeMethod):
+    _kind = cabi.RL_BL
+
+    def __init__(self, Map, max_range, device=-1):
+        super().__init__(Map, max_range, 0, device)
+
+
+class PyRayMarching(_RangeMethod):
+    _kind = cabi.RL_RM
+
+    def __init__(self, Map, max_range, device=-1):
+        super().__init__(Map, max_range, 0, device)
+
+    def distance_transform(self):
+        out = np.empty((self._map.width(), self._map.height()), np.float32)
+        check(lib().rl_debug_get_dt(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+
+class PyRayMarchingGPU(PyRayMarching):
+    """Same backend as PyRayMarching; kept because callers of the reference select the GPU caster
+    by this name (RangeLibc.pyx:313-342)."""
+
+
+class PyCDDTCast(_RangeMethod):
+    _kind = cabi.RL_CDDT
+
+    def __init__(self, Map, max_range, theta_disc, device=-1):
+        self.theta_disc = int(theta_disc)
+        super().__init__(Map, max_range, theta_disc, device)
+
+    def prune(self, max_range=-1.0):
+        check(lib().rl_method_prune(self._h, self.max_range if max_range < 0.0 else float(max_range)))
+
+    def table(self):
+        nb, nv = C.c_int64(), C.c_int64()
+        widths = np.zeros(self.theta_disc, np.int32)
+        trans = np.zeros(self.theta_disc, np.float32)
+        check(lib().rl_debug_cddt_dims(self._h, C.byref(nb), C.byref(nv), C.c_void_p(widths.ctypes.data),
+                                       C.c_void_p(trans.ctypes.data)))
+        offsets = np.zeros(nb.value + 1, np.int64)
+        values = np.zeros(max(nv.value, 1), np.float32)
+        check(lib().rl_debug_cddt_dump(self._h, C.c_void_p(offsets.ctypes.data), C.c_void_p(values.ctypes.data)))
+        return widths, trans, offsets, values[: nv.value]
+
+
+def device_sincosf(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    s = np.empty_like(x)
+    c = np.empty_like(x)
+    check(lib().rl_debug_sincosf(C.c_void_p(x.ctypes.data), C.c_void_p(s.ctypes.data), C.c_void_p(c.ctypes.data),
+                                 x.size))
+    return s, c

@@ -1,0 +1,447 @@
+// extern "C" boundary of librangelib_b200.so (include/rangelib_b200.h).
+// Handles, pointer classification (host vs device), staging for host-pointer calls, dispatch.
+// There is no CPU fallback anywhere in this library: without a usable device every entry point
+// that computes fails with RL_E_NO_DEVICE.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "rl_internal.cuh"
+
+namespace rl {
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  g_err = buf;
+  cudaGetLastError();  // clear sticky-less errors
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? RL_E_NO_DEVICE : RL_E_CUDA;
+}
+
+// 1 = device (or managed), 0 = host, <0 error
+static int is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;  // plain unregistered host memory on old drivers
+  }
+  return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? 1 : 0;
+}
+
+// classify a set of pointers (nullptr entries ignored): 1 all device, 0 all host, RL_E_MIXED
+static int classify(std::initializer_list<const void*> ptrs) {
+  int dev = -1;
+  for (const void* p : ptrs) {
+    if (!p) continue;
+    int d = is_device_ptr(p);
+    if (dev == -1) dev = d;
+    else if (dev != d) {
+      set_error("host and device pointers mixed in one call");
+      return RL_E_MIXED;
+    }
+  }
+  return dev == -1 ? 0 : dev;
+}
+
+static int ensure_stage(rl_method* m, size_t bytes) {
+  if (bytes <= m->d_stage_bytes) return RL_OK;
+  if (m->d_stage) cudaFree(m->d_stage);
+  m->d_stage = nullptr;
+  m->d_stage_bytes = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  RL_CUDA(cudaMalloc(&m->d_stage, want));
+  m->d_stage_bytes = want;
+  return RL_OK;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static int bind(rl_method* m) {
+  if (!m) {
+    set_error("null method handle");
+    return RL_E_INVALID;
+  }
+  RL_CUDA(cudaSetDevice(m->device));
+  return RL_OK;
+}
+
+// Common driver for the four batched cast entry points.
+static int run_cast(rl_method* m, int mode, const float* ins, const float* angles, const float* obs, float* outs,
+                    double* weights, int n, int M) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (n < 0 || M < 0) {
+    set_error("negative count");
+    return RL_E_INVALID;
+  }
+  if (n == 0 || (mode >= MODE_ANGLES && M == 0)) return RL_OK;
+  if (!ins || (mode >= MODE_ANGLES && !angles) || (mode == MODE_FUSED && (!obs || !weights)) ||
+      (mode != MODE_FUSED && !outs)) {
+    set_error("null data pointer");
+    return RL_E_INVALID;
+  }
+  const int side = classify({ins, angles, obs, outs, weights});
+  if (side < 0) return side;
+  if (side == 1) return launch_cast(m, mode, ins, angles, obs, outs, weights, n, M);
+
+  // host pointers: stage in, run, stage out, wait -- blocking like the reference
+  const size_t b_ins = sizeof(float) * 3 * (size_t)n;
+  const size_t b_ang = mode >= MODE_ANGLES ? sizeof(float) * (size_t)M : 0;
+  const size_t b_obs = mode == MODE_FUSED ? sizeof(float) * (size_t)M : 0;
+  const size_t n_out = mode == MODE_ANGLES ? (size_t)n * M : (size_t)n;
+  const size_t b_out = mode == MODE_FUSED ? sizeof(double) * (size_t)n : sizeof(float) * n_out;
+  const size_t o_ins = 0, o_ang = align256(b_ins), o_obs = o_ang + align256(b_ang), o_out = o_obs + align256(b_obs);
+  rc = ensure_stage(m, o_out + align256(b_out));
+  if (rc) return rc;
+  char* base = (char*)m->d_stage;
+  RL_CUDA(cudaMemcpyAsync(base + o_ins, ins, b_ins, cudaMemcpyHostToDevice, m->stream));
+  if (b_ang) RL_CUDA(cudaMemcpyAsync(base + o_ang, angles, b_ang, cudaMemcpyHostToDevice, m->stream));
+  if (b_obs) RL_CUDA(cudaMemcpyAsync(base + o_obs, obs, b_obs, cudaMemcpyHostToDevice, m->stream));
+  rc = launch_cast(m, mode, (const float*)(base + o_ins), (const float*)(base + o_ang), (const float*)(base + o_obs),
+                   (float*)(base + o_out), (double*)(base + o_out), n, M);
+  if (rc) return rc;
+  RL_CUDA(cudaMemcpyAsync(mode == MODE_FUSED ? (void*)weights : (void*)outs, base + o_out, b_out,
+                          cudaMemcpyDeviceToHost, m->stream));
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  return RL_OK;
+}
+
+static void free_method(rl_method* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cddt_free(m);
+  cudaFree(m->d_occ);
+  cudaFree(m->d_bits_y);
+  cudaFree(m->d_dt);
+  cudaFree(m->d_table);
+  cudaFree(m->d_stage);
+  if (m->h_stage) cudaFreeHost(m->h_stage);
+  if (m->ev) cudaEventDestroy(m->ev);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+extern "C" {
+
+const char* rl_last_error(void) { return g_err.c_str(); }
+uint64_t rl_stat_kernel_launches(void) { return g_launches.load(); }
+
+int rl_map_create(const uint8_t* occ, int W, int H, rl_map** out) {
+  if (!out || W < 0 || H < 0 || (!occ && (size_t)W * H > 0)) {
+    set_error("rl_map_create: bad arguments");
+    return RL_E_INVALID;
+  }
+  rl_map* m = new rl_map();
+  m->W = W;
+  m->H = H;
+  m->occ.resize((size_t)W * H);
+  for (size_t i = 0; i < m->occ.size(); ++i) m->occ[i] = occ[i] ? 1 : 0;
+  *out = m;
+  return RL_OK;
+}
+
+int rl_map_set_world(rl_map* map, float scale, float angle, float ox, float oy, float sin_a, float cos_a) {
+  if (!map) {
+    set_error("null map");
+    return RL_E_INVALID;
+  }
+  map->scale = scale;
+  map->angle = angle;
+  map->ox = ox;
+  map->oy = oy;
+  map->sin_a = sin_a;
+  map->cos_a = cos_a;
+  return RL_OK;
+}
+
+int rl_map_width(const rl_map* map) { return map ? map->W : RL_E_INVALID; }
+int rl_map_height(const rl_map* map) { return map ? map->H : RL_E_INVALID; }
+
+int rl_map_is_occupied(const rl_map* map, int x, int y) {
+  if (!map) return RL_E_INVALID;
+  if (x < 0 || x >= map->W || y < 0 || y >= map->H) return 0;
+  return map->occ[(size_t)x * map->H + y];
+}
+
+int rl_map_get(const rl_map* map, uint8_t* out) {
+  if (!map || !out) return RL_E_INVALID;
+  memcpy(out, map->occ.data(), map->occ.size());
+  return RL_OK;
+}
+
+int rl_map_update(rl_map* map, const uint8_t* patch, int x0, int y0, int w, int h) {
+  if (!map || !patch || x0 < 0 || y0 < 0 || w < 0 || h < 0 || x0 + w > map->W || y0 + h > map->H) {
+    set_error("rl_map_update: patch outside the map");
+    return RL_E_INVALID;
+  }
+  for (int x = 0; x < w; ++x)
+    for (int y = 0; y < h; ++y) map->occ[(size_t)(x0 + x) * map->H + (y0 + y)] = patch[(size_t)x * h + y] ? 1 : 0;
+  return RL_OK;
+}
+
+void rl_map_destroy(rl_map* map) { delete map; }
+
+int rl_method_create(int kind, const rl_map* map, float max_range, unsigned td, int device, rl_method** out) {
+  if (!map || !out || kind < RL_BL || kind > RL_PCDDT) {
+    set_error("rl_method_create: bad arguments");
+    return RL_E_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("rangelib_b200 needs a CUDA device (sm_100); there is no CPU fallback");
+    return RL_E_NO_DEVICE;
+  }
+  if (device < 0) RL_CUDA(cudaGetDevice(&device));
+  if (device >= ndev) {
+    set_error("rl_method_create: no such device");
+    return RL_E_INVALID;
+  }
+  int major = 0;
+  RL_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) {
+    set_error("rangelib_b200 is built for sm_100a only; this device is not a B200-class GPU");
+    return RL_E_NO_DEVICE;
+  }
+  RL_CUDA(cudaSetDevice(device));
+  rl_method* m = new rl_method();
+  m->kind = kind;
+  m->device = device;
+  m->W = map->W;
+  m->H = map->H;
+  m->max_range = max_range;
+  m->td = td;
+  // RangeLib.h:442-450
+  m->xf.inv_scale = (float)(1.0 / (double)map->scale);
+  m->xf.scale = map->scale;
+  m->xf.ox = map->ox;
+  m->xf.oy = map->oy;
+  m->xf.sin_a = map->sin_a;
+  m->xf.cos_a = map->cos_a;
+  m->xf.rot = (float)(-1.0 * (double)map->angle - 3.0 * RL_PI / 2.0);
+  int rc = RL_OK;
+  e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) rc = cuda_fail(e, "stream create", __FILE__, __LINE__);
+  m->stream = m->own_stream;
+  if (!rc) rc = upload_occupancy(m, map);
+  if (!rc && kind == RL_RM) rc = build_distance_transform(m);
+  if (!rc && (kind == RL_CDDT || kind == RL_PCDDT)) rc = cddt_build(m);
+  if (!rc && kind == RL_PCDDT) rc = cddt_prune(m, max_range);
+  if (!rc) {
+    e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "method build", __FILE__, __LINE__);
+  }
+  if (rc) {
+    free_method(m);
+    return rc;
+  }
+  *out = m;
+  return RL_OK;
+}
+
+void rl_method_destroy(rl_method* m) { free_method(m); }
+
+int rl_method_prune(rl_method* m, float max_range) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (m->kind != RL_CDDT && m->kind != RL_PCDDT) {
+    set_error("prune is only defined for CDDT");
+    return RL_E_STATE;
+  }
+  return cddt_prune(m, max_range);
+}
+
+int rl_method_set_stream(rl_method* m, void* stream) {
+  if (!m) return RL_E_INVALID;
+  m->stream = stream ? (cudaStream_t)stream : m->own_stream;
+  return RL_OK;
+}
+
+int rl_method_synchronize(rl_method* m) {
+  int rc = bind(m);
+  if (rc) return rc;
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  return RL_OK;
+}
+
+int rl_method_update_map(rl_method* m, const uint8_t* patch, int x0, int y0, int w, int h) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (!patch || x0 < 0 || y0 < 0 || w <= 0 || h <= 0 || x0 + w > m->W || y0 + h > m->H) {
+    set_error("rl_method_update_map: patch outside the map");
+    return RL_E_INVALID;
+  }
+  const uint8_t* d_patch = patch;
+  if (!is_device_ptr(patch)) {
+    rc = ensure_stage(m, (size_t)w * h);
+    if (rc) return rc;
+    RL_CUDA(cudaMemcpyAsync(m->d_stage, patch, (size_t)w * h, cudaMemcpyHostToDevice, m->stream));
+    d_patch = (const uint8_t*)m->d_stage;
+  }
+  rc = apply_patch(m, d_patch, x0, y0, w, h);
+  if (rc) return rc;
+  if (m->kind == RL_RM) rc = build_distance_transform(m);
+  if (m->kind == RL_CDDT || m->kind == RL_PCDDT) {
+    const bool was_pruned = m->pruned;
+    rc = cddt_build(m);
+    if (!rc && was_pruned) rc = cddt_prune(m, m->max_range);
+  }
+  return rc;
+}
+
+int64_t rl_method_memory(const rl_method* m) {
+  if (!m) return RL_E_INVALID;
+  int64_t bytes = (int64_t)m->W * m->H + (int64_t)m->W * m->wpy * 4;
+  if (m->kind == RL_RM) bytes += (int64_t)m->W * m->H * 4;
+  if (m->kind >= RL_CDDT) bytes += m->nvalues * 4 + (m->nbins + 1) * 8 + (int64_t)m->td * 16;
+  return bytes;
+}
+
+int rl_calc_range(rl_method* m, float x, float y, float heading, float* out) {
+  if (!out) return RL_E_INVALID;
+  float in[3] = {x, y, heading};
+  return run_cast(m, MODE_GRID, in, nullptr, nullptr, out, nullptr, 1, 0);
+}
+
+int rl_calc_range_many(rl_method* m, const float* ins, float* outs, int n) {
+  return run_cast(m, MODE_GRID, ins, nullptr, nullptr, outs, nullptr, n, 0);
+}
+
+int rl_numpy_calc_range(rl_method* m, const float* ins, float* outs, int n) {
+  return run_cast(m, MODE_WORLD, ins, nullptr, nullptr, outs, nullptr, n, 0);
+}
+
+int rl_numpy_calc_range_angles(rl_method* m, const float* ins, const float* angles, float* outs, int n, int M) {
+  return run_cast(m, MODE_ANGLES, ins, angles, nullptr, outs, nullptr, n, M);
+}
+
+int rl_set_sensor_model(rl_method* m, const double* table, int k) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (!table || k <= 0) {
+    set_error("set_sensor_model: bad table");
+    return RL_E_INVALID;
+  }
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  if (m->d_table) cudaFree(m->d_table);
+  m->d_table = nullptr;
+  m->K = 0;
+  RL_CUDA(cudaMalloc(&m->d_table, sizeof(double) * (size_t)k * k));
+  RL_CUDA(cudaMemcpyAsync(m->d_table, table, sizeof(double) * (size_t)k * k, cudaMemcpyDefault, m->stream));
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  m->K = k;
+  return RL_OK;
+}
+
+int rl_eval_sensor_model(rl_method* m, const float* obs, const float* ranges, double* outs, int M, int n) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (n < 0 || M < 0) return RL_E_INVALID;
+  if (n == 0) return RL_OK;
+  if (!obs || !ranges || !outs) {
+    if (M == 0 && outs) {
+      // product over zero beams is 1.0 (RangeLib.h:544)
+    } else {
+      set_error("null data pointer");
+      return RL_E_INVALID;
+    }
+  }
+  const int side = classify({obs, ranges, outs});
+  if (side < 0) return side;
+  if (side == 1) return launch_eval_sensor(m, obs, ranges, outs, M, n);
+  const size_t b_obs = sizeof(float) * (size_t)M, b_rng = sizeof(float) * (size_t)n * M, b_out = sizeof(double) * (size_t)n;
+  const size_t o_rng = align256(b_obs), o_out = o_rng + align256(b_rng);
+  rc = ensure_stage(m, o_out + align256(b_out));
+  if (rc) return rc;
+  char* base = (char*)m->d_stage;
+  if (b_obs) RL_CUDA(cudaMemcpyAsync(base, obs, b_obs, cudaMemcpyHostToDevice, m->stream));
+  if (b_rng) RL_CUDA(cudaMemcpyAsync(base + o_rng, ranges, b_rng, cudaMemcpyHostToDevice, m->stream));
+  rc = launch_eval_sensor(m, (const float*)base, (const float*)(base + o_rng), (double*)(base + o_out), M, n);
+  if (rc) return rc;
+  RL_CUDA(cudaMemcpyAsync(outs, base + o_out, b_out, cudaMemcpyDeviceToHost, m->stream));
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  return RL_OK;
+}
+
+int rl_calc_range_repeat_angles_eval_sensor_model(rl_method* m, const float* ins, const float* angles,
+                                                  const float* obs, double* weights, int n, int M) {
+  return run_cast(m, MODE_FUSED, ins, angles, obs, nullptr, weights, n, M);
+}
+
+int rl_debug_get_dt(rl_method* m, float* out) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (m->kind != RL_RM || !m->d_dt || !out) {
+    set_error("rl_debug_get_dt: not an RM method");
+    return RL_E_STATE;
+  }
+  RL_CUDA(cudaMemcpyAsync(out, m->d_dt, sizeof(float) * (size_t)m->W * m->H, cudaMemcpyDeviceToHost, m->stream));
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  return RL_OK;
+}
+
+int rl_debug_cddt_dims(rl_method* m, int64_t* n_bins, int64_t* n_values, int* widths, float* translations) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (m->kind < RL_CDDT) {
+    set_error("not a CDDT method");
+    return RL_E_STATE;
+  }
+  if (n_bins) *n_bins = m->nbins;
+  if (n_values) *n_values = m->nvalues;
+  if (widths) memcpy(widths, m->h_widths.data(), sizeof(int) * m->td);
+  if (translations) memcpy(translations, m->h_trans.data(), sizeof(float) * m->td);
+  return RL_OK;
+}
+
+int rl_debug_cddt_dump(rl_method* m, int64_t* offsets, float* values) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (m->kind < RL_CDDT || !offsets || !values) {
+    set_error("not a CDDT method");
+    return RL_E_STATE;
+  }
+  RL_CUDA(cudaMemcpyAsync(offsets, m->d_offsets, sizeof(int64_t) * ((size_t)m->nbins + 1), cudaMemcpyDeviceToHost, m->stream));
+  if (m->nvalues)
+    RL_CUDA(cudaMemcpyAsync(values, m->d_values, sizeof(float) * (size_t)m->nvalues, cudaMemcpyDeviceToHost, m->stream));
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  return RL_OK;
+}
+
+int rl_debug_sincosf(const float* x, float* s, float* c, int n) {
+  if (n <= 0) return RL_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("rangelib_b200 needs a CUDA device");
+    return RL_E_NO_DEVICE;
+  }
+  float *dx = nullptr, *ds = nullptr, *dc = nullptr;
+  RL_CUDA(cudaMalloc(&dx, sizeof(float) * n));
+  RL_CUDA(cudaMalloc(&ds, sizeof(float) * n));
+  RL_CUDA(cudaMalloc(&dc, sizeof(float) * n));
+  RL_CUDA(cudaMemcpy(dx, x, sizeof(float) * n, cudaMemcpyHostToDevice));
+  int rc = launch_sincosf(dx, ds, dc, n, 0);
+  if (!rc) {
+    RL_CUDA(cudaMemcpy(s, ds, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    RL_CUDA(cudaMemcpy(c, dc, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(dx);
+  cudaFree(ds);
+  cudaFree(dc);
+  return rc;
+}
+
+}  // extern "C"

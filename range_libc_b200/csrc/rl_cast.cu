@@ -1,0 +1,401 @@
+// Batched range queries: the hot path.
+//
+//   cast_kernel<KIND, MODE>   one ray per thread; MODE selects the reference entry point
+//                             GRID   RayMarchingGPU::calc_range_many      RangeLib.h:819-831
+//                             WORLD  RangeMethod::numpy_calc_range        RangeLib.h:439-480
+//                             ANGLES RangeMethod::numpy_calc_range_angles RangeLib.h:482-520
+//   fused_kernel<KIND>        RangeMethod::calc_range_repeat_angles_eval_sensor_model :558-612
+//                             a CTA owns whole particles; ranges go straight to the sensor
+//                             table lookup, the per-particle product is formed in the
+//                             reference's order (beam 0..M-1) so weights are bit-identical
+//   eval_sensor_kernel        RangeMethod::eval_sensor_model              RangeLib.h:533-555
+//
+// KIND: RL_BL (:696-769), RL_RM (:927-962), RL_CDDT / RL_PCDDT (:1342-1516).
+#include "rl_internal.cuh"
+#include "rl_math.cuh"
+
+namespace rl {
+
+// ------------------------------------------------------------------------------------------
+// single-ray device functions
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ bool finite3(float a, float b, float c) {
+  return (fabsf(a) <= 3.402823466e38f) && (fabsf(b) <= 3.402823466e38f) && (fabsf(c) <= 3.402823466e38f);
+}
+
+// RayMarching::calc_range, RangeLib.h:927-962; distThreshold 0.0, step_coeff 0.999f (:967-968)
+__device__ __forceinline__ float rm_cast(const MapView& mv, float max_range, float x0, float y0, float theta) {
+  if (!finite3(x0, y0, theta)) return max_range;  // reference: (int)NaN -> INT_MIN -> out of map
+  float dx, dy;
+  rl_sincosf(theta, &dy, &dx);
+  const unsigned W = (unsigned)mv.W, H = (unsigned)mv.H;
+  const float* __restrict__ dt = mv.dt;
+  float t = 0.0f;
+  while (t < max_range) {
+    int px = __float2int_rz(fadd(x0, fmul(dx, t)));
+    int py = __float2int_rz(fadd(y0, fmul(dy, t)));
+    if ((unsigned)px >= W || (unsigned)py >= H) return max_range;
+    float d = __ldg(dt + (size_t)px * H + py);
+    if (d <= 0.0f) {
+      float xd = fsub((float)px, x0);
+      float yd = fsub((float)py, y0);
+      return __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
+    }
+    t = fadd(t, fmaxf(fmul(d, 0.999f), 1.0f));
+  }
+  return max_range;
+}
+
+__device__ __forceinline__ bool occ_at(const MapView& mv, int x, int y) {  // OMap::isOccupied :204-210
+  if ((unsigned)x >= (unsigned)mv.W || (unsigned)y >= (unsigned)mv.H) return false;
+  return (__ldg(mv.bits_y + (size_t)x * mv.wpy + (y >> 5)) >> (y & 31)) & 1u;
+}
+
+// BresenhamsLine::calc_range, RangeLib.h:696-769.  All state is float, as in the reference; the
+// walk is the reference's recurrence (_x += +-1, error += deltay) step for step.
+__device__ __forceinline__ float bl_cast(const MapView& mv, float max_range, float x, float y, float heading) {
+  if (!finite3(x, y, heading)) return max_range;  // the reference does not terminate on these
+  if (occ_at(mv, f2i(x), f2i(y))) return 0.0f;
+  float sn, cs;
+  rl_sincosf(heading, &sn, &cs);
+  float x0 = y, y0 = x;
+  float x1 = fadd(y, fmul(max_range, sn));
+  float y1 = fadd(x, fmul(max_range, cs));
+  const bool steep = fabsf(fsub(y1, y0)) > fabsf(fsub(x1, x0));
+  if (steep) {
+    float tmp = x0; x0 = y0; y0 = tmp;
+    tmp = x1; x1 = y1; y1 = tmp;
+  }
+  const float deltax = fabsf(fsub(x1, x0)), deltay = fabsf(fsub(y1, y0));
+  float error = 0.0f, _x = x0, _y = y0;
+  const float xstep = (x0 < x1) ? 1.0f : -1.0f;
+  const float ystep = (y0 < y1) ? 1.0f : -1.0f;
+  const int target = f2i(fadd(x1, xstep));
+  // bounds of the float-vs-unsigned compares at :755/:761: not steep -> _y < width, _x < height
+  const float lim_y = steep ? (float)(unsigned)mv.H : (float)(unsigned)mv.W;
+  const float lim_x = steep ? (float)(unsigned)mv.W : (float)(unsigned)mv.H;
+  int guard = f2i(max_range) + 16;  // the walk needs at most deltax + 3 steps
+  while (f2i(_x) != target) {
+    if (--guard < 0) break;
+    _x = fadd(_x, xstep);
+    error = fadd(error, deltay);
+    if (fmul(error, 2.0f) >= deltax) {  // (double)error*2.0 >= (double)deltax: doubling is exact
+      _y = fadd(_y, ystep);
+      error = fsub(error, deltax);
+    }
+    if (0.0f <= _y && _y < lim_y && 0.0f <= _x && _x < lim_x) {
+      int cx = steep ? __float2int_rz(_x) : __float2int_rz(_y);
+      int cy = steep ? __float2int_rz(_y) : __float2int_rz(_x);
+      if (occ_at(mv, cx, cy)) {
+        float xd = fsub(_x, x0), yd = fsub(_y, y0);
+        return __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
+      }
+    }
+  }
+  return max_range;
+}
+
+// CDDTCast::discretize_theta RangeLib.h:1287-1340 (_USE_ALTERNATE_MOD 1, _USE_CACHED_CONSTANTS 1,
+// _USE_FAST_ROUND 0).  The wrap loops add/subtract the double constant and narrow to float each
+// turn exactly as the reference does; they are capped (|theta| beyond ~6000 rad is wrapped with
+// fmod instead -- the reference would spin for that many iterations).
+__device__ __forceinline__ void cddt_discretize(const CddtView& cv, float theta, int* bin, bool* flipped) {
+  if ((double)theta < 0.0) {
+    int it = 0;
+    while ((double)theta < 0.0) {
+      theta = __double2float_rn((double)theta + RL_M_2PI);
+      if (++it > 1000) { theta = __double2float_rn(fmod((double)theta, RL_M_2PI) + RL_M_2PI); }
+    }
+  } else if ((double)theta > RL_M_2PI) {
+    int it = 0;
+    while ((double)theta > RL_M_2PI) {
+      theta = __double2float_rn((double)theta - RL_M_2PI);
+      if (++it > 1000) { theta = __double2float_rn(fmod((double)theta, RL_M_2PI)); }
+    }
+  }
+  bool f = false;
+  if ((double)theta >= RL_PI) {
+    f = true;
+    theta = __double2float_rn((double)theta - RL_PI);
+  }
+  int rounded = (int)roundf(fmul(theta, cv.td_div_2pi));
+  if ((unsigned)rounded == (cv.td >> 1)) {
+    rounded = 0;
+    f = !f;
+  }
+  *bin = (int)((unsigned)rounded % cv.td);
+  *flipped = f;
+}
+
+// CDDTCast::calc_range RangeLib.h:1342-1516.  cos/sin of the discrete angle come from the
+// host-tabulated libm values (cv.cosv/sinv), so trig is out of the parity question.
+__device__ __forceinline__ float cddt_cast(const MapView& mv, const CddtView& cv, float max_range, float x, float y,
+                                           float heading) {
+  if (!finite3(x, y, heading)) return max_range;
+  int a;
+  bool flipped;
+  cddt_discretize(cv, -heading, &a, &flipped);
+  const float ca = __ldg(cv.cosv + a), sa = __ldg(cv.sinv + a);
+  const float lx = fsub(fmul(x, ca), fmul(y, sa));
+  const float ly = fadd(fadd(fmul(x, sa), fmul(y, ca)), __ldg(cv.trans + a));
+  const unsigned li = (unsigned)f2i(ly);
+  if (li >= (unsigned)__ldg(cv.widths + a)) return max_range;
+  const int64_t b = __ldg(cv.slice0 + a) + li;
+  const int64_t o0 = __ldg(cv.offsets + b), o1 = __ldg(cv.offsets + b + 1);
+  const float* __restrict__ B = cv.values + o0;
+  const int size = (int)(o1 - o0);
+  const int high = size - 1;
+  if (high == -1) return max_range;
+  const float first = __ldg(B), last = __ldg(B + high);
+  if (flipped) {
+    if (first > lx) return max_range;
+    if (last < lx) return fsub(lx, last);
+    if (occ_at(mv, f2i(x), f2i(y))) return 0.0f;  // map.grid[x][y] :1413
+    if (high > RL_BINARY_SEARCH_THRESHOLD) {      // std::upper_bound: first element > lx
+      int lo = 0, hi = size;
+      while (lo < hi) {
+        int mid = lo + ((hi - lo) >> 1);
+        if (!(lx < __ldg(B + mid))) lo = mid + 1; else hi = mid;
+      }
+      return fsub(lx, __ldg(B + lo - 1));
+    }
+    for (int i = high; i >= 0; --i) {
+      float v = __ldg(B + i);
+      if (v <= lx) return fsub(lx, v);
+    }
+  } else {
+    if (last < lx) return max_range;
+    if (first > lx) return fsub(first, lx);
+    if (occ_at(mv, f2i(x), f2i(y))) return 0.0f;  // :1475
+    if (high > RL_BINARY_SEARCH_THRESHOLD) {
+      int lo = 0, hi = size;
+      while (lo < hi) {
+        int mid = lo + ((hi - lo) >> 1);
+        if (!(lx < __ldg(B + mid))) lo = mid + 1; else hi = mid;
+      }
+      return fsub(__ldg(B + lo), lx);  // values[] is padded by one float: lo == size reads the pad
+    }
+    for (int i = 0; i < size; ++i) {
+      float v = __ldg(B + i);
+      if (v >= lx) return fsub(v, lx);
+    }
+  }
+  return -1.0f;  // the reference's assert(0) fall-through (:1514)
+}
+
+template <int KIND>
+__device__ __forceinline__ float cast_one(const MapView& mv, const CddtView& cv, float max_range, float x, float y,
+                                          float th) {
+  if (KIND == RL_BL) return bl_cast(mv, max_range, x, y, th);
+  if (KIND == RL_RM) return rm_cast(mv, max_range, x, y, th);
+  return cddt_cast(mv, cv, max_range, x, y, th);
+}
+
+// world -> grid pose, RangeLib.h:464-473.  Returns (x, y, theta) with the reference's names;
+// the caller passes them to calc_range as (y, x, theta) (:475).
+__device__ __forceinline__ void world_to_grid(const WorldXform& xf, float xw, float yw, float thw, float* x, float* y,
+                                              float* th) {
+  float xx = fmul(fsub(xw, xf.ox), xf.inv_scale);
+  float yy = fmul(fsub(yw, xf.oy), xf.inv_scale);
+  float tmp = xx;
+  xx = fsub(fmul(xf.cos_a, xx), fmul(xf.sin_a, yy));
+  yy = fadd(fmul(xf.sin_a, tmp), fmul(xf.cos_a, yy));
+  *x = xx;
+  *y = yy;
+  *th = fadd(-thw, xf.rot);
+}
+
+// clamp + truncate of RangeLib.h:547-551 / 603-606: std::min<float>(std::max<float>(v,0),K-1)
+__device__ __forceinline__ int sensor_index(float v, float kmax) {
+  v = (v < 0.0f) ? 0.0f : v;      // std::max<float>(v, 0.0): (v < 0) ? 0 : v
+  v = (kmax < v) ? kmax : v;      // std::min<float>(v, kmax): (kmax < v) ? kmax : v
+  return __float2int_rz(v);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(256)
+cast_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float* __restrict__ ins,
+            const float* __restrict__ angles, float* __restrict__ outs, long long total, int M) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; r < total; r += stride) {
+    if (MODE == MODE_GRID) {
+      float x = __ldg(ins + 3 * r), y = __ldg(ins + 3 * r + 1), th = __ldg(ins + 3 * r + 2);
+      outs[r] = cast_one<KIND>(mv, cv, max_range, x, y, th);
+    } else if (MODE == MODE_WORLD) {
+      float x, y, th;
+      world_to_grid(xf, __ldg(ins + 3 * r), __ldg(ins + 3 * r + 1), __ldg(ins + 3 * r + 2), &x, &y, &th);
+      outs[r] = fmul(cast_one<KIND>(mv, cv, max_range, y, x, th), xf.scale);
+    } else {
+      long long i = r / M;
+      int a = (int)(r - i * M);
+      float x, y, th;
+      world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
+      outs[r] = fmul(cast_one<KIND>(mv, cv, max_range, y, x, fsub(th, __ldg(angles + a))), xf.scale);
+    }
+  }
+}
+
+// One CTA handles `ppb` consecutive particles per iteration (grid-stride over particle groups).
+// Beams are processed in chunks of at most `chunk` so shared memory stays bounded for any M.
+// smem: double vals[ppb * chunk].
+template <int KIND>
+__global__ void __launch_bounds__(256)
+fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_range, const float* __restrict__ ins,
+             const float* __restrict__ angles, const float* __restrict__ obs, double* __restrict__ weights, int N,
+             int M, int ppb, int chunk) {
+  extern __shared__ double vals[];
+  const float kmax = (float)((double)(float)sv.K - 1.0);
+  const int groups = (N + ppb - 1) / ppb;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int p0 = g * ppb;
+    const int np = min(ppb, N - p0);
+    double w = 1.0;  // running product, owned by thread p < np
+    for (int c0 = 0; c0 < M; c0 += chunk) {
+      const int cm = min(chunk, M - c0);
+      for (int k = threadIdx.x; k < np * cm; k += blockDim.x) {
+        const int p = k / cm, a = c0 + (k - p * cm);
+        const int i = p0 + p;
+        float x, y, th;
+        world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
+        float d = cast_one<KIND>(mv, cv, max_range, y, x, fsub(th, __ldg(angles + a)));
+        const int di = sensor_index(d, kmax);                                   // :602-603 (no scaling)
+        const int ri = sensor_index(fmul(__ldg(obs + a), xf.inv_scale), kmax);  // :605-606
+        vals[p * cm + (a - c0)] = __ldg(sv.table + (size_t)ri * sv.K + di);
+      }
+      __syncthreads();
+      if (threadIdx.x < np) {
+        const double* v = vals + threadIdx.x * cm;
+        for (int a = 0; a < cm; ++a) w = __dmul_rn(w, v[a]);  // reference order: beam ascending
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < np) weights[p0 + threadIdx.x] = w;
+  }
+}
+
+// eval_sensor_model: same epilogue, ranges come from memory (coalesced tile load).
+__global__ void __launch_bounds__(256)
+eval_sensor_kernel(SensorView sv, float inv_scale, const float* __restrict__ obs, const float* __restrict__ ranges,
+                   double* __restrict__ outs, int N, int M, int ppb, int chunk) {
+  extern __shared__ double vals[];
+  const float kmax = (float)((double)(float)sv.K - 1.0);
+  const int groups = (N + ppb - 1) / ppb;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int p0 = g * ppb;
+    const int np = min(ppb, N - p0);
+    double w = 1.0;
+    for (int c0 = 0; c0 < M; c0 += chunk) {
+      const int cm = min(chunk, M - c0);
+      for (int k = threadIdx.x; k < np * cm; k += blockDim.x) {
+        const int p = k / cm, a = c0 + (k - p * cm);
+        const int ri = sensor_index(fmul(__ldg(obs + a), inv_scale), kmax);                       // :547-548
+        const int di = sensor_index(fmul(__ldg(ranges + (size_t)(p0 + p) * M + a), inv_scale), kmax);  // :549-550
+        vals[p * cm + (a - c0)] = __ldg(sv.table + (size_t)ri * sv.K + di);
+      }
+      __syncthreads();
+      if (threadIdx.x < np) {
+        const double* v = vals + threadIdx.x * cm;
+        for (int a = 0; a < cm; ++a) w = __dmul_rn(w, v[a]);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < np) outs[p0 + threadIdx.x] = w;
+  }
+}
+
+__global__ void sincosf_kernel(const float* x, float* s, float* c, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rl_sincosf(x[i], s + i, c + i);
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+template <int KIND>
+static int launch_cast_kind(rl_method* m, int mode, const float* ins, const float* angles, const float* obs,
+                            float* outs, double* weights, int n, int M) {
+  const MapView mv = m->map_view();
+  const CddtView cv = m->cddt_view();
+  const int threads = 256;
+  if (mode == MODE_FUSED) {
+    if (!m->d_table) {
+      set_error("calc_range_repeat_angles_eval_sensor_model: set_sensor_model has not been called");
+      return RL_E_STATE;
+    }
+    const int chunk = min(M, 2048);
+    const int ppb = max(1, min(threads / max(M, 1), 32));
+    const int groups = (n + ppb - 1) / ppb;
+    const int grid = max(1, min(groups, sm_count() * 8));
+    const size_t smem = (size_t)ppb * chunk * sizeof(double);
+    fused_kernel<KIND><<<grid, threads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range, ins, angles,
+                                                           obs, weights, n, M, ppb, chunk);
+  } else {
+    const long long total = (mode == MODE_ANGLES) ? (long long)n * M : (long long)n;
+    const long long blocks = (total + threads - 1) / threads;
+    const int grid = (int)max(1LL, min(blocks, (long long)sm_count() * 8 * 64));
+    if (mode == MODE_GRID)
+      cast_kernel<KIND, MODE_GRID><<<grid, threads, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, total, M);
+    else if (mode == MODE_WORLD)
+      cast_kernel<KIND, MODE_WORLD><<<grid, threads, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, total, M);
+    else
+      cast_kernel<KIND, MODE_ANGLES><<<grid, threads, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, total, M);
+  }
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
+}
+
+int launch_cast(rl_method* m, int mode, const float* ins, const float* angles, const float* obs, float* outs,
+                double* weights, int n, int M) {
+  if (n <= 0 || (mode >= MODE_ANGLES && M <= 0)) return RL_OK;
+  switch (m->kind) {
+    case RL_BL: return launch_cast_kind<RL_BL>(m, mode, ins, angles, obs, outs, weights, n, M);
+    case RL_RM: return launch_cast_kind<RL_RM>(m, mode, ins, angles, obs, outs, weights, n, M);
+    default: return launch_cast_kind<RL_CDDT>(m, mode, ins, angles, obs, outs, weights, n, M);
+  }
+}
+
+int launch_eval_sensor(rl_method* m, const float* obs, const float* ranges, double* outs, int M, int n) {
+  if (n <= 0) return RL_OK;
+  if (!m->d_table) {
+    set_error("eval_sensor_model: set_sensor_model has not been called");
+    return RL_E_STATE;
+  }
+  const int threads = 256;
+  const int chunk = max(1, min(M, 2048));
+  const int ppb = max(1, min(threads / max(M, 1), 32));
+  const int groups = (n + ppb - 1) / ppb;
+  const int grid = max(1, min(groups, sm_count() * 8));
+  const size_t smem = (size_t)ppb * chunk * sizeof(double);
+  eval_sensor_kernel<<<grid, threads, smem, m->stream>>>(m->sensor_view(), m->xf.inv_scale, obs, ranges, outs, n, M,
+                                                         ppb, chunk);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
+}
+
+int launch_sincosf(const float* x, float* s, float* c, int n, cudaStream_t st) {
+  if (n <= 0) return RL_OK;
+  sincosf_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, s, c, n);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
+}
+
+}  // namespace rl

@@ -1,0 +1,138 @@
+// Internal declarations shared by the translation units of librangelib_b200.so.
+// The whole library is compiled with --fmad=false: every float operation in the parity-critical
+// paths rounds exactly like the reference built without FP contraction (the pinned STRICT
+// oracle, see DESIGN.md "Numerics").  Where a fused multiply-add is wanted it is written fma().
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "rangelib_b200.h"
+
+#define RL_EPSILON 0.00001             // RangeLib.h:60
+#define RL_M_2PI 6.28318530718         // RangeLib.h:61
+#define RL_BINARY_SEARCH_THRESHOLD 64  // RangeLib.h:62
+#define RL_PI 3.14159265358979323846   // M_PI
+
+namespace rl {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launch(int n = 1);
+
+#define RL_CUDA(expr)                                                    \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) return rl::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define RL_CHECK_LAUNCH()                                                \
+  do {                                                                   \
+    cudaError_t _e = cudaGetLastError();                                 \
+    if (_e != cudaSuccess) return rl::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+// world -> grid conversion constants, RangeLib.h:442-450
+struct WorldXform {
+  float inv_scale, scale, ox, oy, sin_a, cos_a, rot;
+};
+
+// read-only view of the resident structures handed to kernels
+struct MapView {
+  int W, H;
+  const uint8_t* occ;      // x-major bytes occ[x*H+y]
+  const uint32_t* bits_y;  // bit grid packed along y: word (x, y>>5), bit y&31; row stride wpy words
+  int wpy;
+  const float* dt;         // x-major float distance transform (RM)
+};
+
+struct CddtView {
+  unsigned td;
+  const int* widths;        // [td]
+  const float* trans;       // [td]
+  const float* cosv;        // [td] host-tabulated libm cosf(discrete angle)
+  const float* sinv;        // [td]
+  const int64_t* slice0;    // [td+1]
+  const int64_t* offsets;   // [nbins+1]
+  const float* values;      // [nvalues + pad]
+  float td_div_2pi;         // (float)(td / M_2PI)           RangeLib.h:976
+  float twopi_div_td;       // (float)(M_2PI / (float)td)    RangeLib.h:977
+};
+
+struct SensorView {
+  const double* table;  // K*K row-major table[r*K + d]
+  int K;
+};
+
+enum Mode { MODE_GRID = 0, MODE_WORLD = 1, MODE_ANGLES = 2, MODE_FUSED = 3 };
+
+}  // namespace rl
+
+struct rl_map {
+  int W = 0, H = 0;
+  std::vector<uint8_t> occ;  // x-major
+  float scale = 1.f, angle = 0.f, ox = 0.f, oy = 0.f, sin_a = 0.f, cos_a = 1.f;
+};
+
+struct rl_method {
+  int kind = 0;
+  int device = 0;
+  int W = 0, H = 0;
+  float max_range = 0.f;
+  unsigned td = 0;
+  rl::WorldXform xf{};
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev = nullptr;
+
+  // occupancy on device
+  uint8_t* d_occ = nullptr;
+  uint32_t* d_bits_y = nullptr;
+  int wpy = 0;
+  // RM
+  float* d_dt = nullptr;
+  // CDDT
+  int* d_widths = nullptr;
+  float *d_trans = nullptr, *d_cosv = nullptr, *d_sinv = nullptr;
+  int64_t *d_slice0 = nullptr, *d_offsets = nullptr;
+  float* d_values = nullptr;
+  int64_t nbins = 0, nvalues = 0;
+  std::vector<int> h_widths;
+  std::vector<float> h_trans, h_cosv, h_sinv;
+  std::vector<int64_t> h_slice0;
+  float td_div_2pi = 0.f, twopi_div_td = 0.f;
+  bool pruned = false;
+  // sensor model
+  double* d_table = nullptr;
+  int K = 0;
+  // staging for host-pointer calls
+  void* d_stage = nullptr;
+  size_t d_stage_bytes = 0;
+  void* h_stage = nullptr;  // pinned
+  size_t h_stage_bytes = 0;
+
+  rl::MapView map_view() const { return rl::MapView{W, H, d_occ, d_bits_y, wpy, d_dt}; }
+  rl::CddtView cddt_view() const {
+    return rl::CddtView{td, d_widths, d_trans, d_cosv, d_sinv, d_slice0, d_offsets, d_values, td_div_2pi, twopi_div_td};
+  }
+  rl::SensorView sensor_view() const { return rl::SensorView{d_table, K}; }
+};
+
+namespace rl {
+// rl_edt.cu
+int build_distance_transform(rl_method* m);
+// rl_occ.cu
+int upload_occupancy(rl_method* m, const rl_map* map);
+int apply_patch(rl_method* m, const uint8_t* d_patch, int x0, int y0, int w, int h);
+// rl_cddt.cu
+int cddt_build(rl_method* m);
+int cddt_prune(rl_method* m, float max_range);
+void cddt_free(rl_method* m);
+// rl_cast.cu -- the batched query kernels (all kinds, all modes)
+int launch_cast(rl_method* m, int mode, const float* d_ins, const float* d_angles, const float* d_obs, float* d_outs,
+                double* d_weights, int n, int num_angles);
+int launch_eval_sensor(rl_method* m, const float* d_obs, const float* d_ranges, double* d_outs, int m_rays, int n);
+int launch_sincosf(const float* d_x, float* d_s, float* d_c, int n, cudaStream_t st);
+}  // namespace rl

@@ -1,0 +1,64 @@
+// Occupancy grid residency: byte grid (x-major, the reference's OMap::grid[x][y] order,
+// RangeLib.h:126) plus a bit-packed copy (32 cells of one x-column per word) that the BL walk
+// and the CDDT/BL "standing on an obstacle" test read.  Dynamic maps (BASELINE config 4)
+// patch both on the device.
+#include "rl_internal.cuh"
+
+namespace rl {
+
+// one thread per output word
+__global__ void pack_bits_kernel(const uint8_t* __restrict__ occ, uint32_t* __restrict__ bits, int W, int H, int wpy,
+                                 int x_begin, int x_end, int word_begin, int word_end) {
+  const int nw = word_end - word_begin;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)(x_end - x_begin) * nw;
+  if (idx >= total) return;
+  const int x = x_begin + (int)(idx / nw);
+  const int wd = word_begin + (int)(idx % nw);
+  const int y0 = wd << 5;
+  uint32_t v = 0;
+  const uint8_t* col = occ + (size_t)x * H;
+#pragma unroll 4
+  for (int b = 0; b < 32; ++b) {
+    int y = y0 + b;
+    if (y < H && col[y]) v |= (1u << b);
+  }
+  bits[(size_t)x * wpy + wd] = v;
+}
+
+__global__ void patch_kernel(uint8_t* __restrict__ occ, const uint8_t* __restrict__ patch, int H, int x0, int y0, int w,
+                             int h) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w * h) return;
+  int px = idx / h, py = idx - px * h;
+  occ[(size_t)(x0 + px) * H + (y0 + py)] = patch[idx] ? 1 : 0;
+}
+
+int upload_occupancy(rl_method* m, const rl_map* map) {
+  const size_t n = (size_t)m->W * m->H;
+  m->wpy = (m->H + 31) / 32;
+  RL_CUDA(cudaMalloc(&m->d_occ, n ? n : 1));
+  RL_CUDA(cudaMalloc(&m->d_bits_y, sizeof(uint32_t) * (size_t)m->W * m->wpy + 4));
+  RL_CUDA(cudaMemcpyAsync(m->d_occ, map->occ.data(), n, cudaMemcpyHostToDevice, m->stream));
+  const long long total = (long long)m->W * m->wpy;
+  pack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_y, m->W, m->H, m->wpy, 0,
+                                                                          m->W, 0, m->wpy);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
+}
+
+int apply_patch(rl_method* m, const uint8_t* d_patch, int x0, int y0, int w, int h) {
+  patch_kernel<<<(w * h + 255) / 256, 256, 0, m->stream>>>(m->d_occ, d_patch, m->H, x0, y0, w, h);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  const int wb = y0 >> 5, we = ((y0 + h - 1) >> 5) + 1;
+  const long long total = (long long)w * (we - wb);
+  pack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_y, m->W, m->H, m->wpy,
+                                                                          x0, x0 + w, wb, we);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
+}
+
+}  // namespace rl

@@ -1,0 +1,193 @@
+"""GPU parity: the CUDA path (through the C ABI) against the committed golden vectors of the
+unmodified reference and against the CPU oracle on fresh seeded inputs.
+
+Bars (north_star): BL / CDDT / PCDDT ranges bit-exact; RM bit-exact against the STRICT oracle
+(stated tolerance: 0 differing rays -- device trig restates glibc's sinf/cosf in double);
+distance transform and CDDT/PCDDT tables bit-exact; sensor-model weights bit-exact (the product
+is formed in the reference's order), which is inside the required 1e-5 relative."""
+import numpy as np
+import pytest
+
+import range_libc_b200 as rl
+from range_libc_b200 import api, workloads as wl
+from oracle import port
+from helpers import KINDS, VECTOR_MAPS, assert_bit_equal, golden, world_tuple
+
+pytestmark = pytest.mark.gpu
+
+MR, TD = 500.0, 108
+
+
+def make(kn, occ, max_range=MR, td=TD, world=None):
+    m = rl.PyOMap(np.ascontiguousarray(occ.T.astype(bool)))  # PyOMap takes arr[row=y, col=x]
+    if world is not None:
+        m.set_world(*world)
+    if kn == "bl":
+        return rl.PyBresenhamsLine(m, max_range)
+    if kn == "rm":
+        return rl.PyRayMarchingGPU(m, max_range)
+    c = rl.PyCDDTCast(m, max_range, td)
+    if kn == "pcddt":
+        c.prune()
+    return c
+
+
+def test_device_trig_equals_libm():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-20, 20, 400000), rng.uniform(-130, 130, 100000), rng.uniform(-1e6, 1e6, 20000),
+                        rng.uniform(-1e-3, 1e-3, 1000), np.array([0.0, -0.0, np.pi, 0.75, 0.7853982, 119.99, 120.0, 1e30])
+                        ]).astype(np.float32)
+    s, c = api.device_sincosf(x)
+    es = np.array([port.sinf(v) for v in x[:2000]], np.float32)
+    assert_bit_equal(s[:2000], es, "restated sinf")
+    # numpy's float32 sin/cos are not glibc's; compare against libm through the oracle library
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.sinf.restype = ctypes.c_float
+    libm.sinf.argtypes = [ctypes.c_float]
+    libm.cosf.restype = ctypes.c_float
+    libm.cosf.argtypes = [ctypes.c_float]
+    idx = rng.integers(0, len(x), 50000)
+    idx[-8:] = np.arange(len(x) - 8, len(x))
+    assert_bit_equal(s[idx], np.array([libm.sinf(float(v)) for v in x[idx]], np.float32), "sinf vs libm")
+    assert_bit_equal(c[idx], np.array([libm.cosf(float(v)) for v in x[idx]], np.float32), "cosf vs libm")
+
+
+@pytest.mark.parametrize("name", VECTOR_MAPS)
+@pytest.mark.parametrize("kn", ["bl", "rm", "cddt", "pcddt"])
+def test_golden_vectors(name, kn):
+    g = golden(name)
+    occ = wl.load_map(name)
+    meth = make(kn, occ)
+    q = np.ascontiguousarray(g["queries"])
+    out = np.empty(len(q), np.float32)
+    meth.calc_range_many_grid(q, out)
+    assert_bit_equal(out, g[kn + "_grid"], kn + " grid")
+    parts, angles, obs = (np.ascontiguousarray(g[k]) for k in ("particles", "angles", "obs"))
+    out = np.empty(len(parts) * len(angles), np.float32)
+    meth.calc_range_repeat_angles(parts, angles, out)
+    assert_bit_equal(out, g[kn + "_angles"], kn + " angles")
+    meth.set_sensor_model(wl.sensor_table(501))
+    w = np.empty(len(parts), np.float64)
+    meth.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs, w)
+    assert_bit_equal(w, g[kn + "_weights_fused"], kn + " fused weights")
+    w2 = np.empty(len(parts), np.float64)
+    meth.eval_sensor_model(obs, np.ascontiguousarray(g[kn + "_angles"]), w2, len(angles), len(parts))
+    assert_bit_equal(w2, g[kn + "_weights_two_step"], kn + " two-step weights")
+    for tag in ("world", "world_rot"):
+        mw = make(kn, occ, world=world_tuple(g[tag]))
+        qw = np.ascontiguousarray(g["queries_" + tag])
+        out = np.empty(len(qw), np.float32)
+        mw.calc_range_many(qw, out)
+        assert_bit_equal(out, g[kn + "_" + tag], kn + " " + tag)
+    if kn == "rm":
+        dt = meth.distance_transform()
+        W, H = occ.shape
+        assert_bit_equal(dt[:: max(1, W // 37), :: max(1, H // 41)], g["dt_sample"], "dt sample")
+    if kn in ("cddt", "pcddt"):
+        widths, trans, offsets, values = meth.table()
+        assert (widths == g[kn + "_widths"]).all()
+        assert_bit_equal(trans, g[kn + "_trans"], "translations")
+        assert len(values) == int(g[kn + "_nvalues"])
+
+
+@pytest.mark.parametrize("name", ["basement_hallways_5cm", "basement_fixed_rectangle", "synthetic.map", "small.map",
+                                  "quad.map", "single_pixel.map"])
+def test_structures_equal_oracle(name):
+    """Distance transform and CDDT / PCDDT tables, whole arrays, bit for bit."""
+    occ = wl.load_map(name)
+    assert_bit_equal(make("rm", occ).distance_transform(), port.Oracle(port.RM, occ, MR).dt(), "dt")
+    for kn, kind in (("cddt", port.CDDT), ("pcddt", port.PCDDT)):
+        a = make(kn, occ).table()
+        b = port.Oracle(kind, occ, MR, TD).cddt_table()
+        for x, y, what in zip(a, b, ("widths", "trans", "offsets", "values")):
+            assert_bit_equal(x, y, "%s %s" % (kn, what))
+
+
+@pytest.mark.parametrize("kn", ["bl", "rm", "cddt", "pcddt"])
+def test_fresh_queries_vs_oracle(kn):
+    occ = wl.load_map("basement_hallways_5cm")
+    W, H = occ.shape
+    q = wl.random_queries(W, H, 200000, seed=2024)
+    out = np.empty(len(q), np.float32)
+    make(kn, occ).calc_range_many_grid(q, out)
+    ref = port.Oracle(KINDS[kn], occ, MR, TD, threads=8).calc_range_many(q)
+    assert_bit_equal(out, ref, kn)
+
+
+def test_device_pointers_and_stream():
+    import torch
+    occ = wl.load_map("basement_hallways_10cm")
+    q = wl.random_queries(600, 600, 50000, seed=5)
+    meth = make("rm", occ)
+    host = np.empty(len(q), np.float32)
+    meth.calc_range_many_grid(q, host)
+    dq = torch.from_numpy(q).cuda()
+    dout = torch.empty(len(q), dtype=torch.float32, device="cuda")
+    meth.set_stream(torch.cuda.current_stream().cuda_stream)
+    meth.calc_range_many_grid(dq, dout)
+    torch.cuda.synchronize()
+    assert_bit_equal(dout.cpu().numpy(), host, "device pointers")
+    with pytest.raises(rl.RangeLibError):
+        meth.calc_range_many_grid(dq, host)  # mixed host / device
+
+
+def test_empty_and_ragged_inputs():
+    occ = wl.load_map("basement_hallways_10cm")
+    meth = make("rm", occ)
+    meth.calc_range_many_grid(np.zeros((0, 3), np.float32), np.zeros(0, np.float32))
+    meth.set_sensor_model(wl.sensor_table(501))
+    # one particle, one beam; 3 particles x 70 beams (not a multiple of the warp size)
+    for n, m in ((1, 1), (3, 70), (5, 2500)):
+        parts = wl.pf_particles_uniform(occ, n, seed=n)
+        angles = wl.lidar_angles(m)
+        obs = np.linspace(0, 499, m).astype(np.float32)
+        w = np.empty(n, np.float64)
+        meth.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs, w)
+        o = port.Oracle(port.RM, occ, MR)
+        o.set_sensor_model(wl.sensor_table(501))
+        assert_bit_equal(w, o.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs), "fused %dx%d" % (n, m))
+    with pytest.raises(ValueError):
+        meth.calc_range_many_grid(np.zeros((4, 3), np.float64), np.zeros(4, np.float32))
+    # non-finite poses do not hang and return max_range
+    bad = np.array([[np.nan, 1, 0], [1, np.inf, 0], [10, 10, np.nan]], np.float32)
+    for kn in ("bl", "rm", "cddt"):
+        out = np.empty(3, np.float32)
+        make(kn, occ).calc_range_many_grid(bad, out)
+        assert (out == MR).all()
+
+
+def test_single_ray_api_and_sensor_without_table():
+    occ = wl.load_map("basement_hallways_10cm")
+    meth = make("cddt", occ)
+    o = port.Oracle(port.CDDT, occ, MR, TD)
+    for x, y, th in ((300.5, 290.25, 1.0), (100.0, 100.0, -2.0), (550.0, 20.0, 9.0)):
+        assert np.float32(meth.calc_range(x, y, th)) == np.float32(o.calc_range(x, y, th))
+    with pytest.raises(rl.RangeLibError):
+        meth.eval_sensor_model(np.zeros(2, np.float32), np.zeros(4, np.float32), np.zeros(2, np.float64), 2, 2)
+
+
+def test_dynamic_map_update_bl():
+    occ = wl.synthetic_map(1024, seed=11)
+    meth = make("bl", occ)
+    q = wl.random_queries(1024, 1024, 50000, seed=12)
+    for frame in range(3):
+        for x0, y0, patch in wl.flip_blocks(occ, frame, seed=11, n_blocks=16):
+            meth.update_map(patch, x0, y0)
+        out = np.empty(len(q), np.float32)
+        meth.calc_range_many_grid(q, out)
+        assert_bit_equal(out, port.Oracle(port.BL, occ, MR, threads=8).calc_range_many(q), "frame %d" % frame)
+
+
+def test_dynamic_map_update_rm_and_cddt():
+    occ = wl.synthetic_map(512, seed=21)
+    q = wl.random_queries(512, 512, 20000, seed=22)
+    rm, cd = make("rm", occ), make("pcddt", occ)
+    for x0, y0, patch in wl.flip_blocks(occ, 0, seed=21, n_blocks=8):
+        rm.update_map(patch, x0, y0)
+        cd.update_map(patch, x0, y0)
+    out = np.empty(len(q), np.float32)
+    rm.calc_range_many_grid(q, out)
+    assert_bit_equal(out, port.Oracle(port.RM, occ, MR, threads=8).calc_range_many(q), "rm after update")
+    cd.calc_range_many_grid(q, out)
+    assert_bit_equal(out, port.Oracle(port.PCDDT, occ, MR, TD, threads=8).calc_range_many(q), "pcddt after update")
