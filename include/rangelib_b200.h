@@ -79,8 +79,10 @@ int rl_method_create(int kind, const rl_map* map, float max_range, unsigned thet
 void rl_method_destroy(rl_method* m);
 /* CDDTCast::prune(max_range) RangeLib.h:1176 (PyCDDTCast.prune RangeLibc.pyx:263-267) */
 int rl_method_prune(rl_method* m, float max_range);
-/* run this handle's work on the given cudaStream_t (NULL = the handle's own stream) */
+/* run this handle's work on the given cudaStream_t (0 = CUDA's default stream).  A new handle
+ * runs on a private non-blocking stream until this is called; rl_method_use_own_stream goes back. */
 int rl_method_set_stream(rl_method* m, void* cuda_stream);
+int rl_method_use_own_stream(rl_method* m);
 int rl_method_synchronize(rl_method* m);
 /* dynamic maps: apply an occupancy patch on the device and refresh the structures that depend
  * on it (BL: bit grid only; RM: distance transform rebuilt; CDDT: table rebuilt).
@@ -125,6 +127,11 @@ int rl_debug_get_dt(rl_method* m, float* out);
 int rl_debug_cddt_dims(rl_method* m, int64_t* n_bins, int64_t* n_values, int* widths, float* translations);
 /* offsets: n_bins+1 int64, values: n_values floats; HOST buffers */
 int rl_debug_cddt_dump(rl_method* m, int64_t* offsets, float* values);
+/* tuning knob: look-ahead in px of the creeping-ray L1 prefetch in the RM kernels (0 = off) */
+int rl_debug_set_prefetch(rl_method* m, int px);
+/* tuning knob: RM large batches use persistent warps with lane re-queuing (default 1) or the
+ * one-ray-per-thread kernel (0) */
+int rl_debug_set_persistent(rl_method* m, int on);
 /* device trig used by BL/RM (restated glibc sinf/cosf); HOST buffers; for tests */
 int rl_debug_sincosf(const float* x, float* s, float* c, int n);
 

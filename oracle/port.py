@@ -55,6 +55,7 @@ def _load():
     L.orc_prune_unassigned.argtypes = [C.c_void_p]
     L.orc_calc_range.restype = C.c_float
     L.orc_calc_range.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+    L.orc_rm_step_counts.argtypes = [C.c_void_p, _f32p, _i32p, C.c_int]
     L.orc_dt.restype = _f32p
     L.orc_dt.argtypes = [C.c_void_p]
     for name, rt in [("orc_cddt_nbins", C.c_int64), ("orc_cddt_nvalues", C.c_int64), ("orc_cddt_widths", _i32p),
@@ -170,6 +171,12 @@ class Oracle:
             self.h, _p(ins, _f32p), _p(angles, _f32p), _p(obs, _f32p), _p(w, _f64p), ins.shape[0],
             angles.shape[0], self.threads)
         return w
+
+    def rm_step_counts(self, ins_grid):
+        ins = _f32(ins_grid)
+        out = np.zeros(ins.shape[0], np.int32)
+        self.L.orc_rm_step_counts(self.h, _p(ins, _f32p), _p(out, _i32p), ins.shape[0])
+        return out
 
     def dt(self):
         ptr = self.L.orc_dt(self.h)

@@ -251,6 +251,30 @@ static float rm_calc_range(const orc_ctx* c, float x, float y, float heading) {
   return c->max_range;
 }
 
+/* number of distance-map reads RayMarching::calc_range performs for this ray (analysis aid for
+ * DESIGN.md / bench: the sphere-tracing step count is what bounds the GPU kernels) */
+static int rm_step_count(const orc_ctx* c, float x, float y, float heading) {
+  float x0 = x, y0 = y;
+  float dx = cosf(heading), dy = sinf(heading);
+  float t = 0.0f;
+  int steps = 0;
+  while (t < c->max_range) {
+    int px = (int)(x0 + dx * t);
+    int py = (int)(y0 + dy * t);
+    if (px >= c->W || px < 0 || py < 0 || py >= c->H) return steps;
+    float d = c->dt[(size_t)px * c->H + py];
+    ++steps;
+    if (d <= 0.0f) return steps;
+    float step = d * 0.999f;
+    t += (step > 1.0f ? step : 1.0f);
+  }
+  return steps;
+}
+
+void orc_rm_step_counts(const orc_ctx* c, const float* ins, int* counts, int n) {
+  for (int i = 0; i < n; ++i) counts[i] = rm_step_count(c, ins[3 * i], ins[3 * i + 1], ins[3 * i + 2]);
+}
+
 /* BresenhamsLine::calc_range, RangeLib.h:696-769 */
 static float bl_calc_range(const orc_ctx* c, float x, float y, float heading) {
   if (occ_at(c, (int)x, (int)y)) return 0.0f;

@@ -176,8 +176,12 @@ class _RangeMethod:
 
     # -- extensions ------------------------------------------------------------------------
     def set_stream(self, cuda_stream):
-        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
-        check(lib().rl_method_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream; 0 is the
+        default stream); None goes back to the method's private stream."""
+        if cuda_stream is None:
+            check(lib().rl_method_use_own_stream(self._h))
+        else:
+            check(lib().rl_method_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
     def synchronize(self):
         check(lib().rl_method_synchronize(self._h))
@@ -193,6 +197,14 @@ class _RangeMethod:
 
     def memory(self):
         return int(lib().rl_method_memory(self._h))
+
+    def set_persistent(self, on):
+        """Tuning knob (RM): persistent-warp kernel with lane re-queuing for large batches."""
+        check(lib().rl_debug_set_persistent(self._h, int(on)))
+
+    def set_prefetch(self, px):
+        """Tuning knob (RM): look-ahead in px of the creeping-ray L1 prefetch; 0 disables it."""
+        check(lib().rl_debug_set_prefetch(self._h, int(px)))
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:

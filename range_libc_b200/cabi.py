@@ -30,6 +30,7 @@ SIGNATURES = {
     "rl_method_destroy": (None, [_vp]),
     "rl_method_prune": (_i, [_vp, _f]),
     "rl_method_set_stream": (_i, [_vp, _vp]),
+    "rl_method_use_own_stream": (_i, [_vp]),
     "rl_method_synchronize": (_i, [_vp]),
     "rl_method_update_map": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "rl_method_memory": (C.c_int64, [_vp]),
@@ -44,6 +45,8 @@ SIGNATURES = {
     "rl_debug_cddt_dims": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, _vp]),
     "rl_debug_cddt_dump": (_i, [_vp, _vp, _vp]),
     "rl_debug_sincosf": (_i, [_vp, _vp, _vp, _i]),
+    "rl_debug_set_prefetch": (_i, [_vp, _i]),
+    "rl_debug_set_persistent": (_i, [_vp, _i]),
 }
 
 _lib = None

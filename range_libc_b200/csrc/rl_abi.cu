@@ -24,31 +24,30 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? RL_E_NO_DEVICE : RL_E_CUDA;
 }
 
-// 1 = device (or managed), 0 = host, <0 error
-static int is_device_ptr(const void* p) {
+// where a caller pointer lives
+enum Side { SIDE_PAGEABLE = 0, SIDE_DEVICE = 1, SIDE_PINNED = 2 };
+
+static Side pointer_side(const void* p, void** dev_alias) {
   cudaPointerAttributes at;
   cudaError_t e = cudaPointerGetAttributes(&at, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    return 0;  // plain unregistered host memory on old drivers
+    return SIDE_PAGEABLE;
   }
-  return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? 1 : 0;
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) {
+    if (dev_alias) *dev_alias = const_cast<void*>(p);
+    return SIDE_DEVICE;
+  }
+  if (at.type == cudaMemoryTypeHost && at.devicePointer) {
+    if (dev_alias) *dev_alias = at.devicePointer;
+    return SIDE_PINNED;
+  }
+  return SIDE_PAGEABLE;
 }
 
-// classify a set of pointers (nullptr entries ignored): 1 all device, 0 all host, RL_E_MIXED
-static int classify(std::initializer_list<const void*> ptrs) {
-  int dev = -1;
-  for (const void* p : ptrs) {
-    if (!p) continue;
-    int d = is_device_ptr(p);
-    if (dev == -1) dev = d;
-    else if (dev != d) {
-      set_error("host and device pointers mixed in one call");
-      return RL_E_MIXED;
-    }
-  }
-  return dev == -1 ? 0 : dev;
-}
+static int is_device_ptr(const void* p) { return pointer_side(p, nullptr) == SIDE_DEVICE; }
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static int ensure_stage(rl_method* m, size_t bytes) {
   if (bytes <= m->d_stage_bytes) return RL_OK;
@@ -61,7 +60,18 @@ static int ensure_stage(rl_method* m, size_t bytes) {
   return RL_OK;
 }
 
-static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static int ensure_host_stage(rl_method* m, size_t bytes) {
+  if (bytes <= m->h_stage_bytes) return RL_OK;
+  if (m->h_stage) cudaFreeHost(m->h_stage);
+  m->h_stage = nullptr;
+  m->h_stage_dev = nullptr;
+  m->h_stage_bytes = 0;
+  size_t want = bytes + bytes / 2 + 65536;
+  RL_CUDA(cudaHostAlloc(&m->h_stage, want, cudaHostAllocMapped | cudaHostAllocPortable));
+  RL_CUDA(cudaHostGetDevicePointer(&m->h_stage_dev, m->h_stage, 0));
+  m->h_stage_bytes = want;
+  return RL_OK;
+}
 
 static int bind(rl_method* m) {
   if (!m) {
@@ -71,6 +81,115 @@ static int bind(rl_method* m) {
   RL_CUDA(cudaSetDevice(m->device));
   return RL_OK;
 }
+
+// Marshals the data pointers of one call.
+//   all device             -> run in place, asynchronous
+//   host, small (<= 4 MB)  -> ZERO COPY: the kernel reads the inputs and writes the results
+//                             straight through PCIe from/to pinned host memory.  Caller buffers that
+//                             are already pinned (cudaHostAlloc / cudaHostRegister / torch
+//                             pin_memory) are used in place; pageable ones go through the
+//                             handle's pinned staging buffer with one memcpy each way.  No
+//                             cudaMemcpy is enqueued at all: launch, wait, done.
+//   host, large            -> device staging with async copies on the handle's stream
+// and blocks until the results are in the caller's buffer (the reference's semantics).
+class Marshal {
+ public:
+  static constexpr size_t kZeroCopyLimit = 4u << 20;
+  static constexpr int kMax = 6;
+  explicit Marshal(rl_method* m) : m_(m) {}
+  int add(const void* p, size_t bytes, bool output) {
+    a_[n_] = Arg{const_cast<void*>(p), bytes, output, nullptr, 0, SIDE_PAGEABLE};
+    return n_++;
+  }
+  void* dev(int i) const { return a_[i].dev; }
+  bool on_device() const { return all_device_; }
+
+  int prepare() {
+    int ndev = 0, nhost = 0;
+    size_t total = 0, pageable = 0;
+    for (int i = 0; i < n_; ++i) {
+      Arg& a = a_[i];
+      if (!a.host || a.bytes == 0) continue;
+      a.side = pointer_side(a.host, &a.dev);
+      if (a.side == SIDE_DEVICE) ++ndev; else ++nhost;
+      total += a.bytes;
+      if (a.side == SIDE_PAGEABLE) {
+        a.off = pageable;
+        pageable += align256(a.bytes);
+      }
+    }
+    if (ndev && nhost) {
+      set_error("host and device pointers mixed in one call");
+      return RL_E_MIXED;
+    }
+    all_device_ = nhost == 0;
+    if (all_device_) return RL_OK;
+    zero_copy_ = total <= kZeroCopyLimit;
+    if (zero_copy_) {
+      if (pageable) {
+        int rc = ensure_host_stage(m_, pageable);
+        if (rc) return rc;
+      }
+      for (int i = 0; i < n_; ++i) {
+        Arg& a = a_[i];
+        if (!a.host || a.bytes == 0 || a.side != SIDE_PAGEABLE) continue;
+        if (!a.output) memcpy((char*)m_->h_stage + a.off, a.host, a.bytes);
+        a.dev = (char*)m_->h_stage_dev + a.off;
+      }
+      return RL_OK;
+    }
+    // large: stage everything through device memory
+    size_t off = 0;
+    for (int i = 0; i < n_; ++i) {
+      Arg& a = a_[i];
+      if (!a.host || a.bytes == 0) continue;
+      a.off = off;
+      off += align256(a.bytes);
+    }
+    int rc = ensure_stage(m_, off);
+    if (rc) return rc;
+    for (int i = 0; i < n_; ++i) {
+      Arg& a = a_[i];
+      if (!a.host || a.bytes == 0) continue;
+      a.dev = (char*)m_->d_stage + a.off;
+      if (!a.output) RL_CUDA(cudaMemcpyAsync(a.dev, a.host, a.bytes, cudaMemcpyHostToDevice, m_->stream));
+    }
+    return RL_OK;
+  }
+
+  int finish() {
+    if (all_device_) return RL_OK;
+    if (zero_copy_) {
+      RL_CUDA(cudaStreamSynchronize(m_->stream));
+      for (int i = 0; i < n_; ++i) {
+        Arg& a = a_[i];
+        if (a.host && a.bytes && a.output && a.side == SIDE_PAGEABLE) memcpy(a.host, (char*)m_->h_stage + a.off, a.bytes);
+      }
+      return RL_OK;
+    }
+    for (int i = 0; i < n_; ++i) {
+      Arg& a = a_[i];
+      if (a.host && a.bytes && a.output)
+        RL_CUDA(cudaMemcpyAsync(a.host, a.dev, a.bytes, cudaMemcpyDeviceToHost, m_->stream));
+    }
+    RL_CUDA(cudaStreamSynchronize(m_->stream));
+    return RL_OK;
+  }
+
+ private:
+  struct Arg {
+    void* host;
+    size_t bytes;
+    bool output;
+    void* dev;
+    size_t off;
+    Side side;
+  };
+  rl_method* m_;
+  Arg a_[kMax];
+  int n_ = 0;
+  bool all_device_ = true, zero_copy_ = false;
+};
 
 // Common driver for the four batched cast entry points.
 static int run_cast(rl_method* m, int mode, const float* ins, const float* angles, const float* obs, float* outs,
@@ -87,30 +206,20 @@ static int run_cast(rl_method* m, int mode, const float* ins, const float* angle
     set_error("null data pointer");
     return RL_E_INVALID;
   }
-  const int side = classify({ins, angles, obs, outs, weights});
-  if (side < 0) return side;
-  if (side == 1) return launch_cast(m, mode, ins, angles, obs, outs, weights, n, M);
-
-  // host pointers: stage in, run, stage out, wait -- blocking like the reference
-  const size_t b_ins = sizeof(float) * 3 * (size_t)n;
-  const size_t b_ang = mode >= MODE_ANGLES ? sizeof(float) * (size_t)M : 0;
-  const size_t b_obs = mode == MODE_FUSED ? sizeof(float) * (size_t)M : 0;
   const size_t n_out = mode == MODE_ANGLES ? (size_t)n * M : (size_t)n;
-  const size_t b_out = mode == MODE_FUSED ? sizeof(double) * (size_t)n : sizeof(float) * n_out;
-  const size_t o_ins = 0, o_ang = align256(b_ins), o_obs = o_ang + align256(b_ang), o_out = o_obs + align256(b_obs);
-  rc = ensure_stage(m, o_out + align256(b_out));
+  Marshal ms(m);
+  const int i_ins = ms.add(ins, sizeof(float) * 3 * (size_t)n, false);
+  const int i_ang = ms.add(mode >= MODE_ANGLES ? angles : nullptr, sizeof(float) * (size_t)M, false);
+  const int i_obs = ms.add(mode == MODE_FUSED ? obs : nullptr, sizeof(float) * (size_t)M, false);
+  const int i_out = mode == MODE_FUSED ? ms.add(weights, sizeof(double) * (size_t)n, true)
+                                       : ms.add(outs, sizeof(float) * n_out, true);
+  rc = ms.prepare();
   if (rc) return rc;
-  char* base = (char*)m->d_stage;
-  RL_CUDA(cudaMemcpyAsync(base + o_ins, ins, b_ins, cudaMemcpyHostToDevice, m->stream));
-  if (b_ang) RL_CUDA(cudaMemcpyAsync(base + o_ang, angles, b_ang, cudaMemcpyHostToDevice, m->stream));
-  if (b_obs) RL_CUDA(cudaMemcpyAsync(base + o_obs, obs, b_obs, cudaMemcpyHostToDevice, m->stream));
-  rc = launch_cast(m, mode, (const float*)(base + o_ins), (const float*)(base + o_ang), (const float*)(base + o_obs),
-                   (float*)(base + o_out), (double*)(base + o_out), n, M);
+  rc = launch_cast(m, mode, (const float*)ms.dev(i_ins), (const float*)ms.dev(i_ang), (const float*)ms.dev(i_obs),
+                   mode == MODE_FUSED ? nullptr : (float*)ms.dev(i_out),
+                   mode == MODE_FUSED ? (double*)ms.dev(i_out) : nullptr, n, M);
   if (rc) return rc;
-  RL_CUDA(cudaMemcpyAsync(mode == MODE_FUSED ? (void*)weights : (void*)outs, base + o_out, b_out,
-                          cudaMemcpyDeviceToHost, m->stream));
-  RL_CUDA(cudaStreamSynchronize(m->stream));
-  return RL_OK;
+  return ms.finish();
 }
 
 static void free_method(rl_method* m) {
@@ -265,7 +374,13 @@ int rl_method_prune(rl_method* m, float max_range) {
 
 int rl_method_set_stream(rl_method* m, void* stream) {
   if (!m) return RL_E_INVALID;
-  m->stream = stream ? (cudaStream_t)stream : m->own_stream;
+  m->stream = (cudaStream_t)stream;  // 0 is CUDA's default stream, as everywhere in the runtime API
+  return RL_OK;
+}
+
+int rl_method_use_own_stream(rl_method* m) {
+  if (!m) return RL_E_INVALID;
+  m->stream = m->own_stream;
   return RL_OK;
 }
 
@@ -301,10 +416,22 @@ int rl_method_update_map(rl_method* m, const uint8_t* patch, int x0, int y0, int
   return rc;
 }
 
+int rl_debug_set_prefetch(rl_method* m, int px) {
+  if (!m) return RL_E_INVALID;
+  m->prefetch_px = px < 0 ? 0 : px;
+  return RL_OK;
+}
+
+int rl_debug_set_persistent(rl_method* m, int on) {
+  if (!m) return RL_E_INVALID;
+  m->persist = on;
+  return RL_OK;
+}
+
 int64_t rl_method_memory(const rl_method* m) {
   if (!m) return RL_E_INVALID;
   int64_t bytes = (int64_t)m->W * m->H + (int64_t)m->W * m->wpy * 4;
-  if (m->kind == RL_RM) bytes += (int64_t)m->W * m->H * 4;
+  if (m->kind == RL_RM) bytes += (int64_t)m->dt_elems() * 4;
   if (m->kind >= RL_CDDT) bytes += m->nvalues * 4 + (m->nbins + 1) * 8 + (int64_t)m->td * 16;
   return bytes;
 }
@@ -358,21 +485,15 @@ int rl_eval_sensor_model(rl_method* m, const float* obs, const float* ranges, do
       return RL_E_INVALID;
     }
   }
-  const int side = classify({obs, ranges, outs});
-  if (side < 0) return side;
-  if (side == 1) return launch_eval_sensor(m, obs, ranges, outs, M, n);
-  const size_t b_obs = sizeof(float) * (size_t)M, b_rng = sizeof(float) * (size_t)n * M, b_out = sizeof(double) * (size_t)n;
-  const size_t o_rng = align256(b_obs), o_out = o_rng + align256(b_rng);
-  rc = ensure_stage(m, o_out + align256(b_out));
+  Marshal ms(m);
+  const int i_obs = ms.add(obs, sizeof(float) * (size_t)M, false);
+  const int i_rng = ms.add(ranges, sizeof(float) * (size_t)n * M, false);
+  const int i_out = ms.add(outs, sizeof(double) * (size_t)n, true);
+  rc = ms.prepare();
   if (rc) return rc;
-  char* base = (char*)m->d_stage;
-  if (b_obs) RL_CUDA(cudaMemcpyAsync(base, obs, b_obs, cudaMemcpyHostToDevice, m->stream));
-  if (b_rng) RL_CUDA(cudaMemcpyAsync(base + o_rng, ranges, b_rng, cudaMemcpyHostToDevice, m->stream));
-  rc = launch_eval_sensor(m, (const float*)base, (const float*)(base + o_rng), (double*)(base + o_out), M, n);
+  rc = launch_eval_sensor(m, (const float*)ms.dev(i_obs), (const float*)ms.dev(i_rng), (double*)ms.dev(i_out), M, n);
   if (rc) return rc;
-  RL_CUDA(cudaMemcpyAsync(outs, base + o_out, b_out, cudaMemcpyDeviceToHost, m->stream));
-  RL_CUDA(cudaStreamSynchronize(m->stream));
-  return RL_OK;
+  return ms.finish();
 }
 
 int rl_calc_range_repeat_angles_eval_sensor_model(rl_method* m, const float* ins, const float* angles,
@@ -387,8 +508,12 @@ int rl_debug_get_dt(rl_method* m, float* out) {
     set_error("rl_debug_get_dt: not an RM method");
     return RL_E_STATE;
   }
-  RL_CUDA(cudaMemcpyAsync(out, m->d_dt, sizeof(float) * (size_t)m->W * m->H, cudaMemcpyDeviceToHost, m->stream));
+  std::vector<float> tiled(m->dt_elems());
+  RL_CUDA(cudaMemcpyAsync(tiled.data(), m->d_dt, sizeof(float) * tiled.size(), cudaMemcpyDeviceToHost, m->stream));
   RL_CUDA(cudaStreamSynchronize(m->stream));
+  const int ty = m->dt_tiles_y();
+  for (int x = 0; x < m->W; ++x)
+    for (int y = 0; y < m->H; ++y) out[(size_t)x * m->H + y] = tiled[dt_tiled_index(x, y, ty)];
   return RL_OK;
 }
 

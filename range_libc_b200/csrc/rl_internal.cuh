@@ -40,13 +40,30 @@ struct WorldXform {
   float inv_scale, scale, ox, oy, sin_a, cos_a, rot;
 };
 
+// Distance-transform residency layout.  The grid is cut into tiles of 8 (x) by 4 (y) cells = 32
+// floats = one 128-byte L1/L2 line; inside a tile the cells are bit-interleaved so that each
+// 32-byte sector (the unit the L1 actually fills on a miss) covers a 4x2 block.  A ray that
+// creeps along a wall one pixel at a time therefore stays inside one sector / line for
+// several consecutive sphere-tracing steps whatever its direction, instead of touching a new
+// line on every step as it does in the reference's x-major vector<vector<float>>.
+#define RL_DT_TILE_X_SHIFT 3
+#define RL_DT_TILE_Y_SHIFT 2
+__host__ __device__ __forceinline__ unsigned dt_tiled_index(int px, int py, int tiles_y) {
+  const unsigned ux = (unsigned)px, uy = (unsigned)py;
+  const unsigned tile = (ux >> RL_DT_TILE_X_SHIFT) * (unsigned)tiles_y + (uy >> RL_DT_TILE_Y_SHIFT);
+  const unsigned low = (ux & 3u) | ((uy & 1u) << 2) | ((ux & 4u) << 1) | ((uy & 2u) << 3);
+  return (tile << 5) | low;
+}
+
 // read-only view of the resident structures handed to kernels
 struct MapView {
   int W, H;
   const uint8_t* occ;      // x-major bytes occ[x*H+y]
   const uint32_t* bits_y;  // bit grid packed along y: word (x, y>>5), bit y&31; row stride wpy words
   int wpy;
-  const float* dt;         // x-major float distance transform (RM)
+  const float* dt;         // tiled float distance transform (RM), see dt_tiled_index
+  int dt_tiles_y;
+  int prefetch_px;         // look-ahead (px along the ray) of the creeping-ray L1 prefetch; 0 = off
 };
 
 struct CddtView {
@@ -110,10 +127,16 @@ struct rl_method {
   // staging for host-pointer calls
   void* d_stage = nullptr;
   size_t d_stage_bytes = 0;
-  void* h_stage = nullptr;  // pinned
+  void* h_stage = nullptr;      // pinned + mapped
+  void* h_stage_dev = nullptr;  // its device alias (zero-copy)
   size_t h_stage_bytes = 0;
 
-  rl::MapView map_view() const { return rl::MapView{W, H, d_occ, d_bits_y, wpy, d_dt}; }
+  int dt_tiles_x() const { return (W + 7) >> 3; }
+  int dt_tiles_y() const { return (H + 3) >> 2; }
+  size_t dt_elems() const { return (size_t)dt_tiles_x() * dt_tiles_y() * 32; }
+  int prefetch_px = 6;
+  int persist = 1;  // 0 off, 1 on (8 CTAs/SM), 2 on (6 CTAs/SM, no spills); RM large batches: persistent warps with lane re-queuing (rl_cast.cu)
+  rl::MapView map_view() const { return rl::MapView{W, H, d_occ, d_bits_y, wpy, d_dt, dt_tiles_y(), prefetch_px}; }
   rl::CddtView cddt_view() const {
     return rl::CddtView{td, d_widths, d_trans, d_cosv, d_sinv, d_slice0, d_offsets, d_values, td_div_2pi, twopi_div_td};
   }

@@ -191,3 +191,32 @@ def test_dynamic_map_update_rm_and_cddt():
     assert_bit_equal(out, port.Oracle(port.RM, occ, MR, threads=8).calc_range_many(q), "rm after update")
     cd.calc_range_many_grid(q, out)
     assert_bit_equal(out, port.Oracle(port.PCDDT, occ, MR, TD, threads=8).calc_range_many(q), "pcddt after update")
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_rm_persistent_kernel_large_batches(variant):
+    """Batches large enough for the persistent-warp / lane re-queuing kernel, all three entry points."""
+    occ = wl.load_map("basement_hallways_5cm")
+    W, H = occ.shape
+    world = (0.05, 0.0, -30.0, -30.0, 0.0, 1.0)
+    meth = make("rm", occ, world=world)
+    meth.set_persistent(variant)
+    o = port.Oracle(port.RM, occ, MR, threads=8)
+    o.set_world(*world)
+    n = 1_000_003  # not a multiple of anything
+    q = wl.random_queries(W, H, n, seed=31)
+    out = np.empty(n, np.float32)
+    meth.calc_range_many_grid(q, out)
+    assert_bit_equal(out, o.calc_range_many(q), "grid")
+    qw = wl.grid_to_world(q, world[0], world[2], world[3])
+    meth.calc_range_many(qw, out)
+    assert_bit_equal(out, o.numpy_calc_range(qw), "world")
+    parts = wl.grid_to_world(wl.random_queries(W, H, 9001, seed=32), world[0], world[2], world[3])
+    angles = wl.lidar_angles(113)
+    out = np.empty(len(parts) * len(angles), np.float32)
+    meth.calc_range_repeat_angles(parts, angles, out)
+    assert_bit_equal(out, o.numpy_calc_range_angles(parts, angles), "angles")
+    meth.set_persistent(0)
+    out2 = np.empty_like(out)
+    meth.calc_range_repeat_angles(parts, angles, out2)
+    assert_bit_equal(out2, out, "persistent vs one-ray-per-thread")

@@ -12,7 +12,9 @@ import range_libc_b200 as rl  # noqa: E402
 from range_libc_b200 import workloads as wl  # noqa: E402
 
 
-def timeit(fn, iters=10, warm=3):
+def timeit(fn, iters=10, warm=3, reps=20):
+    """Median / min over `iters` batches of `reps` back-to-back asynchronous launches (per-launch ms):
+    the launches queue up, so host-side call overhead overlaps with the previous kernel."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -20,10 +22,11 @@ def timeit(fn, iters=10, warm=3):
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(reps):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / reps)
     return float(np.median(ts)), float(np.min(ts))
 
 
@@ -32,7 +35,7 @@ def main():
     occ = wl.load_map(name)
     W, H = occ.shape
     omap = rl.PyOMap(np.ascontiguousarray(occ.T.astype(bool)))
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = 0
     t = time.time()
     rm = rl.PyRayMarchingGPU(omap, 500.0)
     t_rm = time.time() - t
