@@ -127,10 +127,11 @@ int rl_debug_get_dt(rl_method* m, float* out);
 int rl_debug_cddt_dims(rl_method* m, int64_t* n_bins, int64_t* n_values, int* widths, float* translations);
 /* offsets: n_bins+1 int64, values: n_values floats; HOST buffers */
 int rl_debug_cddt_dump(rl_method* m, int64_t* offsets, float* values);
-/* tuning knob: look-ahead in px of the creeping-ray L1 prefetch in the RM kernels (0 = off) */
-int rl_debug_set_prefetch(rl_method* m, int px);
-/* tuning knob: RM large batches use persistent warps with lane re-queuing (default 1) or the
- * one-ray-per-thread kernel (0) */
+/* tuning knob (RM): a warp left with at most `lanes` unfinished rays finishes them one at a time with
+ * all 32 lanes cooperating (default 3; 0 = off).  Results are identical. */
+int rl_debug_set_coop_threshold(rl_method* m, int lanes);
+/* tuning knob (RM): large batches use persistent warps with lane re-queuing (default 1) or the
+ * one-ray-per-thread kernel (0).  Results are identical. */
 int rl_debug_set_persistent(rl_method* m, int on);
 /* device trig used by BL/RM (restated glibc sinf/cosf); HOST buffers; for tests */
 int rl_debug_sincosf(const float* x, float* s, float* c, int n);

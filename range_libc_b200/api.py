@@ -202,9 +202,9 @@ class _RangeMethod:
         """Tuning knob (RM): persistent-warp kernel with lane re-queuing for large batches."""
         check(lib().rl_debug_set_persistent(self._h, int(on)))
 
-    def set_prefetch(self, px):
-        """Tuning knob (RM): look-ahead in px of the creeping-ray L1 prefetch; 0 disables it."""
-        check(lib().rl_debug_set_prefetch(self._h, int(px)))
+    def set_coop_threshold(self, lanes):
+        """Tuning knob (RM): warps with <= lanes unfinished rays finish them cooperatively (0 = off)."""
+        check(lib().rl_debug_set_coop_threshold(self._h, int(lanes)))
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:

@@ -63,5 +63,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_cython(force=False):
+    """Builds the drop-in ``range_libc`` extension module (pywrapper/RangeLibc.pyx) against the C ABI."""
+    import sysconfig
+    pyx = os.path.join(HERE, "pywrapper", "RangeLibc.pyx")
+    csrc = os.path.join(HERE, "build", "RangeLibc.c")
+    ext = os.path.join(HERE, "pywrapper", "range_libc" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if not (force or _stale(ext, [pyx, LIB, os.path.join(ROOT, "include", "rangelib_b200.h")])):
+        return ext
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    subprocess.check_call([sys.executable, "-m", "cython", "-3", "--module-name", "range_libc", pyx, "-o", csrc])
+    inc = sysconfig.get_paths()["include"]
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-w", "-I", inc, "-I", os.path.join(ROOT, "include"), csrc,
+                           "-o", ext, "-L", HERE, "-lrangelib_b200", "-Wl,-rpath,$ORIGIN/.."])
+    return ext
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_cython(force="--force" in sys.argv))

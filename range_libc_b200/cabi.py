@@ -45,7 +45,7 @@ SIGNATURES = {
     "rl_debug_cddt_dims": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, _vp]),
     "rl_debug_cddt_dump": (_i, [_vp, _vp, _vp]),
     "rl_debug_sincosf": (_i, [_vp, _vp, _vp, _i]),
-    "rl_debug_set_prefetch": (_i, [_vp, _i]),
+    "rl_debug_set_coop_threshold": (_i, [_vp, _i]),
     "rl_debug_set_persistent": (_i, [_vp, _i]),
 }
 

@@ -4,6 +4,7 @@
 // that computes fails with RL_E_NO_DEVICE.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "rl_internal.cuh"
@@ -84,17 +85,16 @@ static int bind(rl_method* m) {
 
 // Marshals the data pointers of one call.
 //   all device             -> run in place, asynchronous
-//   host, small (<= 4 MB)  -> ZERO COPY: the kernel reads the inputs and writes the results
-//                             straight through PCIe from/to pinned host memory.  Caller buffers that
-//                             are already pinned (cudaHostAlloc / cudaHostRegister / torch
-//                             pin_memory) are used in place; pageable ones go through the
-//                             handle's pinned staging buffer with one memcpy each way.  No
-//                             cudaMemcpy is enqueued at all: launch, wait, done.
-//   host, large            -> device staging with async copies on the handle's stream
+//   host, small (<= 4 MB)  -> the inputs are packed into the handle's pinned staging buffer (one
+//                             memcpy each) and cross PCIe in ONE async copy; the results come back
+//                             in one copy (or, with RL_ZEROCOPY_OUT=1, are written by the kernel
+//                             straight into pinned host memory).  A particle-filter update is
+//                             ~50 KB in / 32 KB out: per-copy latency, not bandwidth, is what costs.
+//   host, large            -> device staging, one async copy per array on the handle's stream
 // and blocks until the results are in the caller's buffer (the reference's semantics).
 class Marshal {
  public:
-  static constexpr size_t kZeroCopyLimit = 4u << 20;
+  static constexpr size_t kSmallLimit = 4u << 20;
   static constexpr int kMax = 6;
   explicit Marshal(rl_method* m) : m_(m) {}
   int add(const void* p, size_t bytes, bool output) {
@@ -105,18 +105,22 @@ class Marshal {
   bool on_device() const { return all_device_; }
 
   int prepare() {
+    static const bool zc_out = getenv("RL_ZEROCOPY_OUT") && atoi(getenv("RL_ZEROCOPY_OUT")) != 0;
     int ndev = 0, nhost = 0;
-    size_t total = 0, pageable = 0;
+    size_t in_bytes = 0, out_bytes = 0;
     for (int i = 0; i < n_; ++i) {
       Arg& a = a_[i];
       if (!a.host || a.bytes == 0) continue;
       a.side = pointer_side(a.host, &a.dev);
       if (a.side == SIDE_DEVICE) ++ndev; else ++nhost;
-      total += a.bytes;
-      if (a.side == SIDE_PAGEABLE) {
-        a.off = pageable;
-        pageable += align256(a.bytes);
-      }
+      // inputs first, then outputs, each 256-byte aligned inside the staging buffers
+      if (!a.output) { a.off = in_bytes; in_bytes += align256(a.bytes); }
+    }
+    for (int i = 0; i < n_; ++i) {
+      Arg& a = a_[i];
+      if (!a.host || a.bytes == 0 || !a.output) continue;
+      a.off = in_bytes + out_bytes;
+      out_bytes += align256(a.bytes);
     }
     if (ndev && nhost) {
       set_error("host and device pointers mixed in one call");
@@ -124,30 +128,28 @@ class Marshal {
     }
     all_device_ = nhost == 0;
     if (all_device_) return RL_OK;
-    zero_copy_ = total <= kZeroCopyLimit;
-    if (zero_copy_) {
-      if (pageable) {
-        int rc = ensure_host_stage(m_, pageable);
-        if (rc) return rc;
-      }
+    in_bytes_ = in_bytes;
+    out_bytes_ = out_bytes;
+    int rc = ensure_stage(m_, in_bytes + out_bytes);
+    if (rc) return rc;
+    small_ = in_bytes + out_bytes <= kSmallLimit;
+    if (small_) {
+      rc = ensure_host_stage(m_, in_bytes + out_bytes);
+      if (rc) return rc;
+      zc_out_ = zc_out;
       for (int i = 0; i < n_; ++i) {
         Arg& a = a_[i];
-        if (!a.host || a.bytes == 0 || a.side != SIDE_PAGEABLE) continue;
-        if (!a.output) memcpy((char*)m_->h_stage + a.off, a.host, a.bytes);
-        a.dev = (char*)m_->h_stage_dev + a.off;
+        if (!a.host || a.bytes == 0) continue;
+        if (!a.output) {
+          memcpy((char*)m_->h_stage + a.off, a.host, a.bytes);
+          a.dev = (char*)m_->d_stage + a.off;
+        } else {
+          a.dev = zc_out_ ? (char*)m_->h_stage_dev + a.off : (char*)m_->d_stage + a.off;
+        }
       }
+      if (in_bytes) RL_CUDA(cudaMemcpyAsync(m_->d_stage, m_->h_stage, in_bytes, cudaMemcpyHostToDevice, m_->stream));
       return RL_OK;
     }
-    // large: stage everything through device memory
-    size_t off = 0;
-    for (int i = 0; i < n_; ++i) {
-      Arg& a = a_[i];
-      if (!a.host || a.bytes == 0) continue;
-      a.off = off;
-      off += align256(a.bytes);
-    }
-    int rc = ensure_stage(m_, off);
-    if (rc) return rc;
     for (int i = 0; i < n_; ++i) {
       Arg& a = a_[i];
       if (!a.host || a.bytes == 0) continue;
@@ -159,11 +161,14 @@ class Marshal {
 
   int finish() {
     if (all_device_) return RL_OK;
-    if (zero_copy_) {
+    if (small_) {
+      if (!zc_out_ && out_bytes_)
+        RL_CUDA(cudaMemcpyAsync((char*)m_->h_stage + in_bytes_, (char*)m_->d_stage + in_bytes_, out_bytes_,
+                                cudaMemcpyDeviceToHost, m_->stream));
       RL_CUDA(cudaStreamSynchronize(m_->stream));
       for (int i = 0; i < n_; ++i) {
         Arg& a = a_[i];
-        if (a.host && a.bytes && a.output && a.side == SIDE_PAGEABLE) memcpy(a.host, (char*)m_->h_stage + a.off, a.bytes);
+        if (a.host && a.bytes && a.output) memcpy(a.host, (char*)m_->h_stage + a.off, a.bytes);
       }
       return RL_OK;
     }
@@ -188,7 +193,8 @@ class Marshal {
   rl_method* m_;
   Arg a_[kMax];
   int n_ = 0;
-  bool all_device_ = true, zero_copy_ = false;
+  size_t in_bytes_ = 0, out_bytes_ = 0;
+  bool all_device_ = true, small_ = false, zc_out_ = false;
 };
 
 // Common driver for the four batched cast entry points.
@@ -416,9 +422,9 @@ int rl_method_update_map(rl_method* m, const uint8_t* patch, int x0, int y0, int
   return rc;
 }
 
-int rl_debug_set_prefetch(rl_method* m, int px) {
+int rl_debug_set_coop_threshold(rl_method* m, int lanes) {
   if (!m) return RL_E_INVALID;
-  m->prefetch_px = px < 0 ? 0 : px;
+  m->coop_threshold = lanes < 0 ? 0 : (lanes > 32 ? 32 : lanes);
   return RL_OK;
 }
 

@@ -24,36 +24,137 @@ __device__ __forceinline__ bool finite3(float a, float b, float c) {
   return (fabsf(a) <= 3.402823466e38f) && (fabsf(b) <= 3.402823466e38f) && (fabsf(c) <= 3.402823466e38f);
 }
 
-// RayMarching::calc_range, RangeLib.h:927-962; distThreshold 0.0, step_coeff 0.999f (:967-968)
-__device__ __forceinline__ float rm_cast(const MapView& mv, float max_range, float x0, float y0, float theta) {
-  if (!finite3(x0, y0, theta)) return max_range;  // reference: (int)NaN -> INT_MIN -> out of map
-  float dx, dy;
-  rl_sincosf(theta, &dy, &dx);
+// ---- RayMarching::calc_range, RangeLib.h:927-962; distThreshold 0.0, step_coeff 0.999f (:967-968) ----
+//
+// rm_step: one iteration of the reference's while loop for one ray (one dependent read of the
+// tiled float distance transform).  Returns true when the ray has ended and `result` is final.
+__device__ __forceinline__ bool rm_step(const MapView& mv, float max_range, float x0, float y0, float dx, float dy,
+                                        float& t, float& result) {
+  const int px = __float2int_rz(fadd(x0, fmul(dx, t)));
+  const int py = __float2int_rz(fadd(y0, fmul(dy, t)));
+  result = max_range;
+  if ((unsigned)px >= (unsigned)mv.W || (unsigned)py >= (unsigned)mv.H) return true;
+  const float d = __ldg(mv.dt + dt_tiled_index(px, py, mv.dt_tiles_y));
+  if (d <= 0.0f) {
+    const float xd = fsub((float)px, x0), yd = fsub((float)py, y0);
+    result = __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
+    return true;
+  }
+  t = fadd(t, fmaxf(fmul(d, 0.999f), 1.0f));
+  return !(t < max_range);
+}
+
+// Cooperative march of ONE ray by all 32 lanes of a warp (same x0, y0, dx, dy, t in every lane).
+//
+// Sphere tracing is a chain of dependent reads: on B200 an L2 hit is ~140 ns and a lone warp
+// needs another ~70 ns of dependent ALU work per step, so a ray that crawls along a wall for
+// 150-300 steps holds its warp -- and, in a small launch such as a 4000 x 60 particle-filter
+// update, the whole kernel -- for 30-60 us while 31 lanes idle.  Here the idle lanes turn the
+// chain into batches: the ray is a straight line, so the cells it can visit over the next
+// ~23 px are known before any distance is.  Lane j reads the distance at parameter
+// t + 0.75 j (one L2 round trip for all 32); the warp then replays the reference's stepping
+// sequence out of registers, finding the cell of each exact sample position
+// (px, py) = (int)(x0 + dx t), (int)(y0 + dy t) among the lanes with a ballot.  A sample whose
+// cell was not prefetched (a corner clipped between two probes, or a jump past the window) just
+// starts the next batch there; lane 0 always probes the exact current sample, so every batch
+// advances at least one step.  Arithmetic and step sequence are the reference's, untouched:
+// the probes are a register-resident cache, never a source of different values.
+#define RL_COOP_SPACING 0.75f
+#define RL_STEP_HIT 0x7f800000u  // +inf: "this cell is an obstacle" in the per-lane step table
+__device__ __forceinline__ float rm_march_coop(const MapView& mv, float max_range, float x0, float y0, float dx,
+                                               float dy, float t) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   const unsigned W = (unsigned)mv.W, H = (unsigned)mv.H;
-  const float* __restrict__ dt = mv.dt;
-  float t = 0.0f;
-  while (t < max_range) {
-    int px = __float2int_rz(fadd(x0, fmul(dx, t)));
-    int py = __float2int_rz(fadd(y0, fmul(dy, t)));
-    if ((unsigned)px >= W || (unsigned)py >= H) return max_range;
-    float d = __ldg(dt + dt_tiled_index(px, py, mv.dt_tiles_y));
-    if (d <= 0.0f) {
-      float xd = fsub((float)px, x0);
-      float yd = fsub((float)py, y0);
+  while (true) {
+    // ---- probe batch: lane j reads the cell at parameter t + 0.75 j and keeps the step it implies ----
+    const float s = t + (float)lane * RL_COOP_SPACING;  // lane 0: exactly t
+    const int cx = __float2int_rz(fadd(x0, fmul(dx, s)));
+    const int cy = __float2int_rz(fadd(y0, fmul(dy, s)));
+    int key = -1;
+    unsigned stepbits = 0u;
+    if ((unsigned)cx < W && (unsigned)cy < H) {
+      key = (cx << 16) | cy;  // map sides are < 32768 when this path is enabled
+      const float d = __ldg(mv.dt + dt_tiled_index(cx, cy, mv.dt_tiles_y));
+      stepbits = (d <= 0.0f) ? RL_STEP_HIT : __float_as_uint(fmaxf(fmul(d, 0.999f), 1.0f));
+    }
+    // ---- replay the reference's steps out of the probes: one warp-wide max-reduction per step.
+    // The loop has a single exit test; a sample whose cell was not probed, a sample outside the map and
+    // an obstacle all add +inf to t and are told apart afterwards.
+    float tp;
+    unsigned r;
+    int px, py;
+    do {
+      tp = t;
+      px = __float2int_rz(fadd(x0, fmul(dx, t)));
+      py = __float2int_rz(fadd(y0, fmul(dy, t)));
+      const int k0 = ((unsigned)px < W && (unsigned)py < H) ? ((px << 16) | py) : -2;
+      r = __reduce_max_sync(FULL, key == k0 ? stepbits : 0u);
+      t = fadd(t, __uint_as_float(r ? r : RL_STEP_HIT));
+    } while (t < max_range);
+    if ((unsigned)px >= W || (unsigned)py >= H) return max_range;  // left the map (RangeLib.h:942-944)
+    if (r == RL_STEP_HIT) {                                        // d <= distThreshold (:952-956)
+      const float xd = fsub((float)px, x0), yd = fsub((float)py, y0);
       return __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
     }
-    t = fadd(t, fmaxf(fmul(d, 0.999f), 1.0f));
-    // Creeping along a wall (small d => ~1 px steps): the ray is straight, so the cells it will
-    // sample a few steps from now are known.  Pull their sector into L1 now so the dependent
-    // load of that later step is an L1 hit (~30 cycles) instead of an L2 round trip (~300).
-    if (mv.prefetch_px > 0 && d < 4.0f) {
-      const float ta = t + (float)mv.prefetch_px;
-      const int qx = __float2int_rz(x0 + dx * ta), qy = __float2int_rz(y0 + dy * ta);
-      if ((unsigned)qx < W && (unsigned)qy < H)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(dt + dt_tiled_index(qx, qy, mv.dt_tiles_y)));
+    if (r != 0u) return max_range;  // a real step carried t to max_range (:938)
+    t = tp;                         // cell not probed: next batch starts at this sample
+  }
+}
+
+// Marches the rays held by the lanes of one warp to completion.  Must be called by all 32 lanes.
+// While many lanes hold a live ray every lane steps its own ray (rm_step) in short divergent
+// bursts; once at most mv.coop_threshold remain, they are finished one after the other by
+// rm_march_coop.
+#define RL_BURST 8
+__device__ __forceinline__ float rm_march_warp(const MapView& mv, float max_range, bool active, float x0, float y0,
+                                               float dx, float dy) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  float t = 0.0f, result = max_range;
+  const int coop = (mv.W < 32768 && mv.H < 32768) ? mv.coop_threshold : 0;
+  while (true) {
+    unsigned act = __ballot_sync(FULL, active);
+    if (!act) break;
+    if (__popc(act) <= coop) {
+      while (act) {
+        const int src = __ffs(act) - 1;
+        act &= act - 1;
+        const float r = rm_march_coop(mv, max_range, __shfl_sync(FULL, x0, src), __shfl_sync(FULL, y0, src),
+                                      __shfl_sync(FULL, dx, src), __shfl_sync(FULL, dy, src),
+                                      __shfl_sync(FULL, t, src));
+        if (lane == src) result = r;
+      }
+      break;
+    }
+    if (active) {
+      int n = RL_BURST;
+      bool done;
+      do {
+        done = rm_step(mv, max_range, x0, y0, dx, dy, t, result);
+      } while (!done && --n);
+      active = !done;
     }
   }
-  return max_range;
+  return result;
+}
+
+// pose -> ray; `ok` false for non-finite poses and for max_range <= 0 (the reference's loop body
+// never runs / (int)NaN leaves the map: both return max_range)
+__device__ __forceinline__ bool rm_setup(float max_range, float x, float y, float theta, float* dx, float* dy) {
+  if (!finite3(x, y, theta) || !(0.0f < max_range)) return false;
+  rl_sincosf(theta, dy, dx);
+  return true;
+}
+
+// single-thread form (kept for callers that cannot guarantee a converged warp)
+__device__ __forceinline__ float rm_cast(const MapView& mv, float max_range, float x0, float y0, float theta) {
+  float dx, dy;
+  if (!rm_setup(max_range, x0, y0, theta, &dx, &dy)) return max_range;
+  float t = 0.0f, result;
+  while (!rm_step(mv, max_range, x0, y0, dx, dy, t, result)) {
+  }
+  return result;
 }
 
 __device__ __forceinline__ bool occ_at(const MapView& mv, int x, int y) {  // OMap::isOccupied :204-210
@@ -225,28 +326,143 @@ __device__ __forceinline__ int sensor_index(float v, float kmax) {
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
+
+// resolves ray r of a batch into the pose handed to calc_range, per entry point
+template <int MODE>
+__device__ __forceinline__ void load_pose(const WorldXform& xf, const float* __restrict__ ins,
+                                          const float* __restrict__ angles, long long r, int M, float* gx, float* gy,
+                                          float* gth) {
+  if (MODE == MODE_GRID) {
+    *gx = __ldg(ins + 3 * r);
+    *gy = __ldg(ins + 3 * r + 1);
+    *gth = __ldg(ins + 3 * r + 2);
+  } else {
+    const long long i = (MODE == MODE_ANGLES) ? r / M : r;
+    float x, y, th;
+    world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
+    if (MODE == MODE_ANGLES) th = fsub(th, __ldg(angles + (int)(r - i * M)));
+    *gx = y;  // calc_range(y, x, theta): RangeLib.h:475 / :518
+    *gy = x;
+    *gth = th;
+  }
+}
+
+// one ray per thread, grid-stride; the loop is warp-uniform so that RM can march at warp level
 template <int KIND, int MODE>
 __global__ void __launch_bounds__(256)
 cast_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float* __restrict__ ins,
             const float* __restrict__ angles, float* __restrict__ outs, long long total, int M) {
-  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; r < total; r += stride) {
-    if (MODE == MODE_GRID) {
-      float x = __ldg(ins + 3 * r), y = __ldg(ins + 3 * r + 1), th = __ldg(ins + 3 * r + 2);
-      outs[r] = cast_one<KIND>(mv, cv, max_range, x, y, th);
-    } else if (MODE == MODE_WORLD) {
-      float x, y, th;
-      world_to_grid(xf, __ldg(ins + 3 * r), __ldg(ins + 3 * r + 1), __ldg(ins + 3 * r + 2), &x, &y, &th);
-      outs[r] = fmul(cast_one<KIND>(mv, cv, max_range, y, x, th), xf.scale);
+  const long long first = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);  // this warp's first ray
+  const int lane = threadIdx.x & 31;
+  for (long long base = first; base < total; base += stride) {
+    const long long r = base + lane;
+    const bool valid = r < total;
+    float gx = 0.f, gy = 0.f, gth = 0.f;
+    if (valid) load_pose<MODE>(xf, ins, angles, r, M, &gx, &gy, &gth);
+    float range;
+    if (KIND == RL_RM) {
+      float dx = 0.f, dy = 0.f;
+      const bool ok = valid && rm_setup(max_range, gx, gy, gth, &dx, &dy);
+      range = rm_march_warp(mv, max_range, ok, gx, gy, dx, dy);
     } else {
-      long long i = r / M;
-      int a = (int)(r - i * M);
-      float x, y, th;
-      world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
-      outs[r] = fmul(cast_one<KIND>(mv, cv, max_range, y, x, fsub(th, __ldg(angles + a))), xf.scale);
+      range = valid ? cast_one<KIND>(mv, cv, max_range, gx, gy, gth) : 0.0f;
     }
+    if (valid) outs[r] = (MODE == MODE_GRID) ? range : fmul(range, xf.scale);
   }
+}
+
+// One CTA handles `ppb` consecutive particles per iteration (grid-stride over particle groups).
+// Beams are processed in chunks of at most `chunk` so shared memory stays bounded for any M.
+// smem: double vals[ppb * chunk].
+template <int KIND>
+__global__ void __launch_bounds__(256)
+fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_range, const float* __restrict__ ins,
+             const float* __restrict__ angles, const float* __restrict__ obs, double* __restrict__ weights, int N,
+             int M, int ppb, int chunk) {
+  extern __shared__ double vals[];
+  const float kmax = (float)((double)(float)sv.K - 1.0);
+  const int groups = (N + ppb - 1) / ppb;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int p0 = g * ppb;
+    const int np = min(ppb, N - p0);
+    double w = 1.0;  // running product, owned by thread p < np
+    for (int c0 = 0; c0 < M; c0 += chunk) {
+      const int cm = min(chunk, M - c0);
+      const int rays = np * cm;
+      for (int k0 = 0; k0 < rays; k0 += blockDim.x) {  // block-uniform trip count
+        const int k = k0 + threadIdx.x;
+        const bool valid = k < rays;
+        int p = 0, a = c0;
+        float gx = 0.f, gy = 0.f, gth = 0.f;
+        if (valid) {
+          p = k / cm;
+          a = c0 + (k - p * cm);
+          const int i = p0 + p;
+          float x, y, th;
+          world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
+          gx = y;
+          gy = x;
+          gth = fsub(th, __ldg(angles + a));
+        }
+        float d;
+        if (KIND == RL_RM) {
+          float dx = 0.f, dy = 0.f;
+          const bool ok = valid && rm_setup(max_range, gx, gy, gth, &dx, &dy);
+          d = rm_march_warp(mv, max_range, ok, gx, gy, dx, dy);
+        } else {
+          d = valid ? cast_one<KIND>(mv, cv, max_range, gx, gy, gth) : 0.0f;
+        }
+        if (valid) {
+          const int di = sensor_index(d, kmax);                                   // :602-603 (no scaling)
+          const int ri = sensor_index(fmul(__ldg(obs + a), xf.inv_scale), kmax);  // :605-606
+          vals[p * cm + (a - c0)] = __ldg(sv.table + (size_t)ri * sv.K + di);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < np) {
+        const double* v = vals + threadIdx.x * cm;
+        for (int a = 0; a < cm; ++a) w = __dmul_rn(w, v[a]);  // reference order: beam ascending
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < np) weights[p0 + threadIdx.x] = w;
+  }
+}
+
+// eval_sensor_model: same epilogue, ranges come from memory (coalesced tile load).
+__global__ void __launch_bounds__(256)
+eval_sensor_kernel(SensorView sv, float inv_scale, const float* __restrict__ obs, const float* __restrict__ ranges,
+                   double* __restrict__ outs, int N, int M, int ppb, int chunk) {
+  extern __shared__ double vals[];
+  const float kmax = (float)((double)(float)sv.K - 1.0);
+  const int groups = (N + ppb - 1) / ppb;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int p0 = g * ppb;
+    const int np = min(ppb, N - p0);
+    double w = 1.0;
+    for (int c0 = 0; c0 < M; c0 += chunk) {
+      const int cm = min(chunk, M - c0);
+      for (int k = threadIdx.x; k < np * cm; k += blockDim.x) {
+        const int p = k / cm, a = c0 + (k - p * cm);
+        const int ri = sensor_index(fmul(__ldg(obs + a), inv_scale), kmax);                            // :547-548
+        const int di = sensor_index(fmul(__ldg(ranges + (size_t)(p0 + p) * M + a), inv_scale), kmax);  // :549-550
+        vals[p * cm + (a - c0)] = __ldg(sv.table + (size_t)ri * sv.K + di);
+      }
+      __syncthreads();
+      if (threadIdx.x < np) {
+        const double* v = vals + threadIdx.x * cm;
+        for (int a = 0; a < cm; ++a) w = __dmul_rn(w, v[a]);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < np) outs[p0 + threadIdx.x] = w;
+  }
+}
+
+__global__ void sincosf_kernel(const float* x, float* s, float* c, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rl_sincosf(x[i], s + i, c + i);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -265,8 +481,8 @@ cast_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float
 // ------------------------------------------------------------------------------------------
 #define RL_QB 4  // parked rays per lane and setup phase
 
-template <int MODE, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template <int MODE>
+__global__ void __launch_bounds__(256, 6)
 rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __restrict__ ins,
                   const float* __restrict__ angles, float* __restrict__ outs, long long total, int M, int chunk) {
   __shared__ float4 q_all[8 * RL_QB * 32];
@@ -277,9 +493,6 @@ rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
   const long long begin = warp_global * chunk;
   const long long end = min(begin + (long long)chunk, total);
   if (begin >= end) return;
-  const unsigned W = (unsigned)mv.W, H = (unsigned)mv.H;
-  const float* __restrict__ dt = mv.dt;
-  const int tiles_y = mv.dt_tiles_y;
   const float out_scale = (MODE == MODE_GRID) ? 1.0f : xf.scale;
 
   // all ray bookkeeping is relative to `begin` (chunk <= 2^20) to keep the state in 32-bit registers
@@ -305,19 +518,7 @@ rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
         for (int e = lane; e < batch_n; e += 32) {
           const long long r = begin + batch_base + e;
           float gx, gy, gth;
-          if (MODE == MODE_GRID) {
-            gx = __ldg(ins + 3 * r);
-            gy = __ldg(ins + 3 * r + 1);
-            gth = __ldg(ins + 3 * r + 2);
-          } else {
-            const long long i = (MODE == MODE_ANGLES) ? r / M : r;
-            float x, y, th;
-            world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
-            if (MODE == MODE_ANGLES) th = fsub(th, __ldg(angles + (int)(r - i * M)));
-            gx = y;  // calc_range(y, x, theta), RangeLib.h:475 / :518
-            gy = x;
-            gth = th;
-          }
+          load_pose<MODE>(xf, ins, angles, r, M, &gx, &gy, &gth);
           float4 ray;
           if (finite3(gx, gy, gth)) {
             float sn, cs;
@@ -346,100 +547,15 @@ rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
     }
     if (!__any_sync(FULL, active)) break;
     if (active) {
-      // one step of RayMarching::calc_range (RangeLib.h:938-959)
-      const int px = __float2int_rz(fadd(x0, fmul(dx, t)));
-      const int py = __float2int_rz(fadd(y0, fmul(dy, t)));
-      float result = max_range;
-      bool done = true;
-      if ((unsigned)px < W && (unsigned)py < H) {
-        const float d = __ldg(dt + dt_tiled_index(px, py, tiles_y));
-        if (d <= 0.0f) {
-          const float xd = fsub((float)px, x0), yd = fsub((float)py, y0);
-          result = __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
-        } else {
-          t = fadd(t, fmaxf(fmul(d, 0.999f), 1.0f));
-          done = !(t < max_range);
-        }
-      }
+      // one iteration of RayMarching::calc_range's loop (RangeLib.h:938-959)
+      float result;
+      const bool done = rm_step(mv, max_range, x0, y0, dx, dy, t, result);
       if (done) {
         outs[id] = (MODE == MODE_GRID) ? result : fmul(result, out_scale);
         active = false;
       }
     }
   }
-}
-
-// One CTA handles `ppb` consecutive particles per iteration (grid-stride over particle groups).
-// Beams are processed in chunks of at most `chunk` so shared memory stays bounded for any M.
-// smem: double vals[ppb * chunk].
-template <int KIND>
-__global__ void __launch_bounds__(256)
-fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_range, const float* __restrict__ ins,
-             const float* __restrict__ angles, const float* __restrict__ obs, double* __restrict__ weights, int N,
-             int M, int ppb, int chunk) {
-  extern __shared__ double vals[];
-  const float kmax = (float)((double)(float)sv.K - 1.0);
-  const int groups = (N + ppb - 1) / ppb;
-  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
-    const int p0 = g * ppb;
-    const int np = min(ppb, N - p0);
-    double w = 1.0;  // running product, owned by thread p < np
-    for (int c0 = 0; c0 < M; c0 += chunk) {
-      const int cm = min(chunk, M - c0);
-      for (int k = threadIdx.x; k < np * cm; k += blockDim.x) {
-        const int p = k / cm, a = c0 + (k - p * cm);
-        const int i = p0 + p;
-        float x, y, th;
-        world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
-        float d = cast_one<KIND>(mv, cv, max_range, y, x, fsub(th, __ldg(angles + a)));
-        const int di = sensor_index(d, kmax);                                   // :602-603 (no scaling)
-        const int ri = sensor_index(fmul(__ldg(obs + a), xf.inv_scale), kmax);  // :605-606
-        vals[p * cm + (a - c0)] = __ldg(sv.table + (size_t)ri * sv.K + di);
-      }
-      __syncthreads();
-      if (threadIdx.x < np) {
-        const double* v = vals + threadIdx.x * cm;
-        for (int a = 0; a < cm; ++a) w = __dmul_rn(w, v[a]);  // reference order: beam ascending
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x < np) weights[p0 + threadIdx.x] = w;
-  }
-}
-
-// eval_sensor_model: same epilogue, ranges come from memory (coalesced tile load).
-__global__ void __launch_bounds__(256)
-eval_sensor_kernel(SensorView sv, float inv_scale, const float* __restrict__ obs, const float* __restrict__ ranges,
-                   double* __restrict__ outs, int N, int M, int ppb, int chunk) {
-  extern __shared__ double vals[];
-  const float kmax = (float)((double)(float)sv.K - 1.0);
-  const int groups = (N + ppb - 1) / ppb;
-  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
-    const int p0 = g * ppb;
-    const int np = min(ppb, N - p0);
-    double w = 1.0;
-    for (int c0 = 0; c0 < M; c0 += chunk) {
-      const int cm = min(chunk, M - c0);
-      for (int k = threadIdx.x; k < np * cm; k += blockDim.x) {
-        const int p = k / cm, a = c0 + (k - p * cm);
-        const int ri = sensor_index(fmul(__ldg(obs + a), inv_scale), kmax);                       // :547-548
-        const int di = sensor_index(fmul(__ldg(ranges + (size_t)(p0 + p) * M + a), inv_scale), kmax);  // :549-550
-        vals[p * cm + (a - c0)] = __ldg(sv.table + (size_t)ri * sv.K + di);
-      }
-      __syncthreads();
-      if (threadIdx.x < np) {
-        const double* v = vals + threadIdx.x * cm;
-        for (int a = 0; a < cm; ++a) w = __dmul_rn(w, v[a]);
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x < np) outs[p0 + threadIdx.x] = w;
-  }
-}
-
-__global__ void sincosf_kernel(const float* x, float* s, float* c, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) rl_sincosf(x[i], s + i, c + i);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -478,23 +594,17 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     const long long total = (mode == MODE_ANGLES) ? (long long)n * M : (long long)n;
     // RM with enough rays to give every resident warp more than one ray per lane: persistent
     // warps with lane re-queuing.  (max_range <= 0 never enters the marching loop.)
-    const long long resident_warps = (long long)sm_count() * 64;
+    const long long resident_warps = (long long)sm_count() * 48;
     if (KIND == RL_RM && m->max_range > 0.0f && total >= resident_warps * 64 && m->persist) {
       long long per_warp = (total + resident_warps - 1) / resident_warps;
       const int chunk = (int)min((long long)1 << 20, ((per_warp + 31) / 32) * 32);
       const long long warps = (total + chunk - 1) / chunk;
       const int grid = (int)((warps + 7) / 8);
-#define RL_LAUNCH_PERSIST(MD, MB) \
-  rm_persist_kernel<MD, MB><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk)
-      if (m->persist == 2) {
-        if (mode == MODE_GRID) RL_LAUNCH_PERSIST(MODE_GRID, 6);
-        else if (mode == MODE_WORLD) RL_LAUNCH_PERSIST(MODE_WORLD, 6);
-        else RL_LAUNCH_PERSIST(MODE_ANGLES, 6);
-      } else {
-        if (mode == MODE_GRID) RL_LAUNCH_PERSIST(MODE_GRID, 8);
-        else if (mode == MODE_WORLD) RL_LAUNCH_PERSIST(MODE_WORLD, 8);
-        else RL_LAUNCH_PERSIST(MODE_ANGLES, 8);
-      }
+#define RL_LAUNCH_PERSIST(MD) \
+  rm_persist_kernel<MD><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk)
+      if (mode == MODE_GRID) RL_LAUNCH_PERSIST(MODE_GRID);
+      else if (mode == MODE_WORLD) RL_LAUNCH_PERSIST(MODE_WORLD);
+      else RL_LAUNCH_PERSIST(MODE_ANGLES);
 #undef RL_LAUNCH_PERSIST
       count_launch();
       RL_CHECK_LAUNCH();

@@ -63,7 +63,7 @@ struct MapView {
   int wpy;
   const float* dt;         // tiled float distance transform (RM), see dt_tiled_index
   int dt_tiles_y;
-  int prefetch_px;         // look-ahead (px along the ray) of the creeping-ray L1 prefetch; 0 = off
+  int coop_threshold;      // RM: warps with at most this many live rays finish them cooperatively (0 = off)
 };
 
 struct CddtView {
@@ -134,9 +134,9 @@ struct rl_method {
   int dt_tiles_x() const { return (W + 7) >> 3; }
   int dt_tiles_y() const { return (H + 3) >> 2; }
   size_t dt_elems() const { return (size_t)dt_tiles_x() * dt_tiles_y() * 32; }
-  int prefetch_px = 6;
-  int persist = 1;  // 0 off, 1 on (8 CTAs/SM), 2 on (6 CTAs/SM, no spills); RM large batches: persistent warps with lane re-queuing (rl_cast.cu)
-  rl::MapView map_view() const { return rl::MapView{W, H, d_occ, d_bits_y, wpy, d_dt, dt_tiles_y(), prefetch_px}; }
+  int coop_threshold = 3;
+  int persist = 1;  // RM large batches: 0 one ray per thread, 1 persistent warps with lane re-queuing
+  rl::MapView map_view() const { return rl::MapView{W, H, d_occ, d_bits_y, wpy, d_dt, dt_tiles_y(), coop_threshold}; }
   rl::CddtView cddt_view() const {
     return rl::CddtView{td, d_widths, d_trans, d_cosv, d_sinv, d_slice0, d_offsets, d_values, td_div_2pi, twopi_div_td};
   }

@@ -17,15 +17,15 @@ omap = rl.PyOMap(np.ascontiguousarray(occ.T.astype(bool)))
 rm = rl.PyRayMarchingGPU(omap, 500.0)
 rm.set_stream(0)
 rm.set_sensor_model(wl.sensor_table(501))
-for N in (1 << 20, 1 << 22, 1 << 24, 1 << 26):
+for N in (1 << 18, 1 << 22, 1 << 24, 1 << 26):
     q = torch.from_numpy(wl.random_queries(W, H, N, seed=1)).cuda()
     out = torch.empty(N, dtype=torch.float32, device="cuda")
-    for pv in (0, 1, 2):
+    for pv in (0, 1):
         rm.set_persistent(pv)
-        for pf in (0, 6):
-            rm.set_prefetch(pf)
+        for coop in (0, 3):
+            rm.set_coop_threshold(coop)
             med, mn = timeit(lambda: rm.calc_range_many_grid(q, out))
-            print("RM random N=%9d persist=%d prefetch=%d  %8.3f ms %7.2f G rays/s" % (N, pv, pf, med, N / med / 1e6))
+            print("RM random N=%9d persist=%d coop=%d  %8.3f ms %7.2f G rays/s" % (N, pv, coop, med, N / med / 1e6))
     del q, out
 rm.set_persistent(1)
 dt = rm.distance_transform()
@@ -37,9 +37,9 @@ for (n, M) in ((4000, 60), (100000, 60), (20000, 1080)):
         obs = torch.from_numpy(np.linspace(5, 450, M).astype(np.float32)).cuda()
         w = torch.empty(n, dtype=torch.float64, device="cuda")
         rng = torch.empty(n * M, dtype=torch.float32, device="cuda")
-        for pf in (0, 2, 4, 6, 8, 12, 16):
-            rm.set_prefetch(pf)
+        for coop in (0, 1, 2, 3, 4, 6, 8, 12):
+            rm.set_coop_threshold(coop)
             med, mn = timeit(lambda: rm.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs, w), iters=20)
             med2, mn2 = timeit(lambda: rm.calc_range_repeat_angles(parts, angles, rng), iters=20)
-            print("PF %7dx%4d %-8s prefetch=%2d fused %8.3f ms (min %.3f, %6.2f G rays/s) | angles %8.3f ms (%6.2f G rays/s)" % (
-                n, M, tag, pf, med, mn, n * M / med / 1e6, med2, n * M / med2 / 1e6))
+            print("PF %7dx%4d %-8s coop=%2d fused %8.3f ms (min %.3f, %6.2f G rays/s) | angles %8.3f ms (%6.2f G rays/s)" % (
+                n, M, tag, coop, med, mn, n * M / med / 1e6, med2, n * M / med2 / 1e6))
