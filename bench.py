@@ -207,7 +207,26 @@ def main():
 
     set_views = [sets[i] for i in range(n_sets)]
 
+    # multi-GPU: the fused kernel stores its weights into every rank's gathered array over NVLink (symmetric
+    # memory) and a symmetric-memory barrier closes the step; NCCL all-gather is the fallback
+    peer, gather_mode = None, "none (single GPU)"
+    if world > 1:
+        gather_mode = "nccl all_gather_into_tensor"
+        if os.environ.get("RL_BENCH_GATHER", "peer") == "peer":
+            try:
+                from range_libc_b200 import parallel
+                peer = parallel.PeerStoreSensorUpdate(world * N_PART, rm, angles, obs, device=dev)
+                peer.update(set_views[0])
+                torch.cuda.synchronize()
+                gather_mode = "fused kernel epilogue: peer stores over NVLink into symmetric memory + symm barrier"
+            except Exception as ex:  # noqa: BLE001
+                peer = None
+                gather_mode = "nccl all_gather_into_tensor (symmetric memory unavailable: %s)" % str(ex).splitlines()[0][:100]
+
     def step(i):
+        if peer is not None:
+            peer.update(set_views[i % n_sets])
+            return
         rm.calc_range_repeat_angles_eval_sensor_model(set_views[i % n_sets], angles, obs, my_w)
         if world > 1:
             dist.all_gather_into_tensor(weights_all, my_w)
@@ -227,6 +246,8 @@ def main():
     # ~10 us kernel) and replayed inside the event-bracketed region; eager launches are the fallback.
     graph, mode = None, "eager"
     try:
+        if world > 1 and peer is None:
+            raise RuntimeError("NCCL collectives are launched eagerly (no graph capture)")
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(stream)
         graph = torch.cuda.CUDAGraph()
@@ -302,20 +323,33 @@ def main():
     cold_ms = float(np.mean(cold))
     del flush
 
-    # end to end through the public API with HOST buffers: pinned inputs, H2D + kernel + D2H inside the timed region
+    # end to end through the public API with HOST buffers: pinned inputs, H2D + kernel + D2H inside the timed region.
+    # The public API is the drop-in Cython module `range_libc` (same names as the reference's module); the ctypes
+    # mirror is used if the extension has not been built.
     rm.set_stream(None)
+    e2e_api = "range_libc_b200.PyRayMarchingGPU.calc_range_repeat_angles_eval_sensor_model(numpy host arrays)"
+    rm_e2e = rm
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "range_libc_b200", "pywrapper"))
+        import range_libc as cy
+        cy_map = cy.PyOMap(np.ascontiguousarray(occ.T.astype(bool)))
+        rm_e2e = cy.PyRayMarchingGPU(cy_map, MAX_RANGE)
+        rm_e2e.set_sensor_model(table)
+        e2e_api = "range_libc.PyRayMarchingGPU.calc_range_repeat_angles_eval_sensor_model(numpy host arrays) [Cython drop-in]"
+    except ImportError:
+        pass
     n_host_sets = 64
     host_sets = [torch.from_numpy(sets_h[i].copy()).pin_memory().numpy() for i in range(n_host_sets)]
     host_angles = torch.from_numpy(angles_h.copy()).pin_memory().numpy()
     host_obs = torch.from_numpy(obs_h.copy()).pin_memory().numpy()
     host_w = torch.empty(N_PART, dtype=torch.float64).pin_memory().numpy()
     for i in range(W_):
-        rm.calc_range_repeat_angles_eval_sensor_model(host_sets[i % n_host_sets], host_angles, host_obs, host_w)
+        rm_e2e.calc_range_repeat_angles_eval_sensor_model(host_sets[i % n_host_sets], host_angles, host_obs, host_w)
     barrier()
     ke = min(K_, 2000)
     t0 = time.perf_counter()
     for i in range(ke):
-        rm.calc_range_repeat_angles_eval_sensor_model(host_sets[i % n_host_sets], host_angles, host_obs, host_w)
+        rm_e2e.calc_range_repeat_angles_eval_sensor_model(host_sets[i % n_host_sets], host_angles, host_obs, host_w)
         if world > 1:
             my_w.copy_(torch.from_numpy(host_w), non_blocking=True)
             dist.all_gather_into_tensor(weights_all, my_w)
@@ -349,13 +383,14 @@ def main():
                          "measurement" % (n_sets, n_sets * N_PART * 12 / 1e6)},
         "gpu_launches": int(launches),
         "launch_mode": mode,
+        "weight_gather": gather_mode,
         "ms_per_step_eager": eager_ms,
         "kernel_ms": kernel_ms,
         "value_cold_l2": N_PART * N_BEAMS / (cold_ms * 1e-3),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 12 * N_PART + 8 * N_BEAMS,
                 "d2h_bytes_per_step": 8 * N_PART, "ms_per_step": e2e_s / ke * 1e3, "steps": ke,
-                "api": "PyRayMarchingGPU.calc_range_repeat_angles_eval_sensor_model(numpy host arrays)"},
+                "api": e2e_api},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "fused_kernel<RM>", "algorithmic_bytes_per_launch": algo_bytes,
                      "peak_source": peak_src,

@@ -118,6 +118,17 @@ int rl_calc_range_repeat_angles_eval_sensor_model(rl_method* m, const float* ins
                                                   const float* obs, double* weights, int num_particles,
                                                   int num_angles);
 
+/* Multi-GPU form of the fused call (one process per GPU, particles sharded across ranks, map and
+ * tables replicated): the kernel's epilogue stores this rank's `num_particles` weights directly into
+ * the gathered weight array of EVERY rank -- peer_weights[r] is rank r's array as a peer-mapped
+ * device pointer (e.g. torch symmetric memory / cudaIpc / cuMem fabric handle), written at
+ * [offset, offset + num_particles).  The compute and the all-gather are one kernel; the caller only
+ * needs a cross-rank barrier before reading.  Device pointers only; asynchronous on the handle's
+ * stream.  (No counterpart in the reference, which is single-GPU.) */
+int rl_calc_range_repeat_angles_eval_sensor_model_peers(rl_method* m, const float* ins, const float* angles,
+                                                        const float* obs, double* const* peer_weights, int n_peers,
+                                                        int64_t offset, int num_particles, int num_angles);
+
 /* ---- table-level access for parity tests ---------------------------------------------------- */
 /* distance transform, x-major out[x*H+y] (DistanceTransform::grid RangeLib.h:328); RL_RM only. out: HOST */
 int rl_debug_get_dt(rl_method* m, float* out);

@@ -156,6 +156,18 @@ class _RangeMethod:
             raise ValueError("shape mismatch")
         check(lib().rl_calc_range_repeat_angles_eval_sensor_model(self._h, pi, pa, pb, pw, si[0], sa[0]))
 
+    def calc_range_repeat_angles_eval_sensor_model_peers(self, ins, angles, obs, peer_ptrs, offset):
+        """Multi-GPU fused update: weights of the local particles `ins` are stored by the kernel into every
+        rank's gathered array (peer_ptrs: one peer-mapped device pointer per rank) at `offset`."""
+        pi, si = _buf(ins, np.float32, 2, "ins")
+        pa, sa = _buf(angles, np.float32, 1, "angles")
+        pb, sb = _buf(obs, np.float32, 1, "obs")
+        if si[1] != 3 or sb[0] < sa[0]:
+            raise ValueError("shape mismatch")
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        check(lib().rl_calc_range_repeat_angles_eval_sensor_model_peers(self._h, pi, pa, pb, arr, len(peer_ptrs),
+                                                                        int(offset), si[0], sa[0]))
+
     def eval_sensor_model(self, observation, ranges, outs, num_rays, num_particles):
         pb, sb = _buf(observation, np.float32, 1, "observation")
         pr, sr = _buf(ranges, np.float32, 1, "ranges")

@@ -41,6 +41,7 @@ SIGNATURES = {
     "rl_set_sensor_model": (_i, [_vp, _vp, _i]),
     "rl_eval_sensor_model": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
     "rl_calc_range_repeat_angles_eval_sensor_model": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "rl_calc_range_repeat_angles_eval_sensor_model_peers": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_vp), _i, C.c_int64, _i, _i]),
     "rl_debug_get_dt": (_i, [_vp, _vp]),
     "rl_debug_cddt_dims": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, _vp]),
     "rl_debug_cddt_dump": (_i, [_vp, _vp, _vp]),

@@ -507,6 +507,41 @@ int rl_calc_range_repeat_angles_eval_sensor_model(rl_method* m, const float* ins
   return run_cast(m, MODE_FUSED, ins, angles, obs, nullptr, weights, n, M);
 }
 
+int rl_calc_range_repeat_angles_eval_sensor_model_peers(rl_method* m, const float* ins, const float* angles,
+                                                        const float* obs, double* const* peer_weights, int n_peers,
+                                                        int64_t offset, int n, int M) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (n < 0 || M < 0 || n_peers < 1 || n_peers > RL_MAX_PEERS || !peer_weights || offset < 0) {
+    set_error("rl_calc_range_repeat_angles_eval_sensor_model_peers: bad arguments");
+    return RL_E_INVALID;
+  }
+  if (n == 0) return RL_OK;
+  if (!ins || !angles || !obs) {
+    set_error("null data pointer");
+    return RL_E_INVALID;
+  }
+  if (!is_device_ptr(ins) || !is_device_ptr(angles) || !is_device_ptr(obs)) {
+    set_error("the peer-store variant takes device pointers only");
+    return RL_E_MIXED;
+  }
+  PeerOut po;
+  po.n = n_peers;
+  po.offset = offset;
+  for (int r = 0; r < n_peers; ++r) {
+    if (!peer_weights[r]) {
+      set_error("null peer buffer");
+      return RL_E_INVALID;
+    }
+    po.ptr[r] = peer_weights[r];
+  }
+  if (M == 0) {
+    set_error("num_angles must be > 0 for the peer-store variant");
+    return RL_E_INVALID;
+  }
+  return launch_cast(m, MODE_FUSED, ins, angles, obs, nullptr, nullptr, n, M, &po);
+}
+
 int rl_debug_get_dt(rl_method* m, float* out) {
   int rc = bind(m);
   if (rc) return rc;

@@ -379,7 +379,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256)
 fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_range, const float* __restrict__ ins,
              const float* __restrict__ angles, const float* __restrict__ obs, double* __restrict__ weights, int N,
-             int M, int ppb, int chunk) {
+             int M, int ppb, int chunk, PeerOut peers) {
   extern __shared__ double vals[];
   const float kmax = (float)((double)(float)sv.K - 1.0);
   const int groups = (N + ppb - 1) / ppb;
@@ -426,7 +426,13 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
       }
       __syncthreads();
     }
-    if (threadIdx.x < np) weights[p0 + threadIdx.x] = w;
+    if (threadIdx.x < np) {
+      if (peers.n == 0) {
+        weights[p0 + threadIdx.x] = w;
+      } else {  // all-gather by direct peer stores (NVLink): every GPU gets this rank's slice
+        for (int r = 0; r < peers.n; ++r) peers.ptr[r][peers.offset + p0 + threadIdx.x] = w;
+      }
+    }
   }
 }
 
@@ -574,7 +580,7 @@ static int sm_count() {
 
 template <int KIND>
 static int launch_cast_kind(rl_method* m, int mode, const float* ins, const float* angles, const float* obs,
-                            float* outs, double* weights, int n, int M) {
+                            float* outs, double* weights, int n, int M, const PeerOut* peers) {
   const MapView mv = m->map_view();
   const CddtView cv = m->cddt_view();
   const int threads = 256;
@@ -588,8 +594,12 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     const int groups = (n + ppb - 1) / ppb;
     const int grid = max(1, min(groups, sm_count() * 8));
     const size_t smem = (size_t)ppb * chunk * sizeof(double);
+    PeerOut po;
+    po.n = 0;
+    po.offset = 0;
+    if (peers) po = *peers;
     fused_kernel<KIND><<<grid, threads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range, ins, angles,
-                                                           obs, weights, n, M, ppb, chunk);
+                                                           obs, weights, n, M, ppb, chunk, po);
   } else {
     const long long total = (mode == MODE_ANGLES) ? (long long)n * M : (long long)n;
     // RM with enough rays to give every resident warp more than one ray per lane: persistent
@@ -625,12 +635,12 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
 }
 
 int launch_cast(rl_method* m, int mode, const float* ins, const float* angles, const float* obs, float* outs,
-                double* weights, int n, int M) {
+                double* weights, int n, int M, const PeerOut* peers) {
   if (n <= 0 || (mode >= MODE_ANGLES && M <= 0)) return RL_OK;
   switch (m->kind) {
-    case RL_BL: return launch_cast_kind<RL_BL>(m, mode, ins, angles, obs, outs, weights, n, M);
-    case RL_RM: return launch_cast_kind<RL_RM>(m, mode, ins, angles, obs, outs, weights, n, M);
-    default: return launch_cast_kind<RL_CDDT>(m, mode, ins, angles, obs, outs, weights, n, M);
+    case RL_BL: return launch_cast_kind<RL_BL>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
+    case RL_RM: return launch_cast_kind<RL_RM>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
+    default: return launch_cast_kind<RL_CDDT>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
   }
 }
 

@@ -86,6 +86,16 @@ struct SensorView {
 
 enum Mode { MODE_GRID = 0, MODE_WORLD = 1, MODE_ANGLES = 2, MODE_FUSED = 3 };
 
+// Multi-GPU epilogue of the fused kernel: instead of one local array, the per-particle weights are
+// stored straight into the weight buffer of every peer GPU (peer-mapped device pointers over
+// NVLink), at this rank's offset -- the all-gather is the kernel's own store phase.
+#define RL_MAX_PEERS 16
+struct PeerOut {
+  double* ptr[RL_MAX_PEERS];
+  int n;             // 0: write only the local `weights` array
+  long long offset;  // first particle of this rank inside the gathered array
+};
+
 }  // namespace rl
 
 struct rl_map {
@@ -155,7 +165,7 @@ int cddt_prune(rl_method* m, float max_range);
 void cddt_free(rl_method* m);
 // rl_cast.cu -- the batched query kernels (all kinds, all modes)
 int launch_cast(rl_method* m, int mode, const float* d_ins, const float* d_angles, const float* d_obs, float* d_outs,
-                double* d_weights, int n, int num_angles);
+                double* d_weights, int n, int num_angles, const PeerOut* peers = nullptr);
 int launch_eval_sensor(rl_method* m, const float* d_obs, const float* d_ranges, double* d_outs, int m_rays, int n);
 int launch_sincosf(const float* d_x, float* d_s, float* d_c, int n, cudaStream_t st);
 }  // namespace rl

@@ -1,0 +1,93 @@
+"""Multi-GPU particle-filter sensor update: one process per GPU, particles sharded across ranks, the
+map / distance transform / sensor table replicated, per-particle weights gathered on every rank
+(SURVEY.md section 8e).  Plain ray batches need no collective; only the weights are exchanged.
+
+Two gather paths:
+  * "peer":  the fused kernel's epilogue stores each weight straight into every rank's gathered
+             array over NVLink (rl_calc_range_repeat_angles_eval_sensor_model_peers); the arrays
+             live in torch symmetric memory, and a symmetric-memory barrier orders the step.
+  * "nccl":  local fused kernel, then torch.distributed.all_gather_into_tensor (NCCL on GPUs;
+             gloo in the CPU tests, where the compute callable is injected).
+The host-side logic here (slicing, gather bookkeeping, uneven shards) has no GPU dependency so that
+it can be exercised with world_size-2 gloo tests.
+"""
+import numpy as np
+
+
+def particle_slice(n_total, rank, world):
+    """Contiguous shard [lo, hi) of rank `rank`; the first n_total % world ranks get one extra."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n_total, world):
+    return [particle_slice(n_total, r, world)[1] - particle_slice(n_total, r, world)[0] for r in range(world)]
+
+
+class ShardedSensorUpdate:
+    """weights_all = update(local_particles): every rank returns the weights of ALL particles.
+
+    compute(local_particles, out_local) must fill out_local (1-D float64 tensor view of this rank's
+    slice) with the fused range + sensor-model weights of the local particles."""
+
+    def __init__(self, n_total, compute, group=None, device=None, dtype=None):
+        import torch
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_total = n_total
+        self.lo, self.hi = particle_slice(n_total, self.rank, self.world)
+        self.sizes = shard_sizes(n_total, self.world)
+        self.compute = compute
+        self.even = len(set(self.sizes)) == 1
+        self.weights_all = torch.empty(n_total, dtype=dtype or torch.float64, device=device)
+        if not self.even:  # all_gather with uneven shards: pad to the largest shard
+            self.pad = max(self.sizes)
+            self.stage_local = torch.zeros(self.pad, dtype=self.weights_all.dtype, device=device)
+            self.stage_all = torch.empty(self.pad * self.world, dtype=self.weights_all.dtype, device=device)
+
+    def local_view(self):
+        return self.weights_all[self.lo:self.hi]
+
+    def update(self, local_particles):
+        self.compute(local_particles, self.local_view())
+        if self.world == 1:
+            return self.weights_all
+        if self.even:
+            self.dist.all_gather_into_tensor(self.weights_all, self.local_view(), group=self.group)
+        else:
+            self.stage_local[: self.hi - self.lo].copy_(self.local_view())
+            self.dist.all_gather_into_tensor(self.stage_all, self.stage_local, group=self.group)
+            for r in range(self.world):
+                lo, hi = particle_slice(self.n_total, r, self.world)
+                self.weights_all[lo:hi].copy_(self.stage_all[r * self.pad: r * self.pad + (hi - lo)])
+        return self.weights_all
+
+
+class PeerStoreSensorUpdate:
+    """Fused compute + all-gather: the weights array lives in torch symmetric memory and the RM kernel
+    writes each rank's slice into every peer directly.  GPU only."""
+
+    def __init__(self, n_total, method, angles, obs, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.dist = dist
+        self.group = group or dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n_total = n_total
+        self.lo, self.hi = particle_slice(n_total, self.rank, self.world)
+        self.method, self.angles, self.obs = method, angles, obs
+        self.weights_all = symm_mem.empty(n_total, dtype=torch.float64, device=device)
+        self.handle = symm_mem.rendezvous(self.weights_all, self.group)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def update(self, local_particles):
+        self.method.calc_range_repeat_angles_eval_sensor_model_peers(local_particles, self.angles, self.obs,
+                                                                     self.peer_ptrs, self.lo)
+        self.handle.barrier()  # every rank's stores have landed before anyone reads weights_all
+        return self.weights_all

@@ -1,0 +1,65 @@
+"""Run under torchrun on >= 2 GPUs:  torchrun --nproc-per-node 2 tests/multi_gpu_check.py
+Checks the sharded fused sensor update (peer-store epilogue and the NCCL path) against the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import range_libc_b200 as rl  # noqa: E402
+from range_libc_b200 import parallel, workloads as wl  # noqa: E402
+from oracle import port  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    local = int(os.environ["LOCAL_RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    occ = wl.load_map("basement_hallways_5cm")
+    n_total, M = 4001, 60
+    particles = wl.pf_particles_uniform(occ, n_total, seed=5)
+    angles_h = wl.lidar_angles(M)
+    obs_h = np.linspace(10, 400, M).astype(np.float32)
+    table = wl.sensor_table(501)
+    omap = rl.PyOMap(np.ascontiguousarray(occ.T.astype(bool)))
+    rm = rl.PyRayMarchingGPU(omap, 500.0, device=local)
+    rm.set_sensor_model(table)
+    rm.set_stream(torch.cuda.current_stream().cuda_stream)
+    angles = torch.from_numpy(angles_h).to(dev)
+    obs = torch.from_numpy(obs_h).to(dev)
+    lo, hi = parallel.particle_slice(n_total, rank, world)
+    mine = torch.from_numpy(particles[lo:hi]).to(dev)
+    ora = port.Oracle(port.RM, occ, 500.0, threads=4)
+    ora.set_sensor_model(table)
+    ref = ora.calc_range_repeat_angles_eval_sensor_model(particles, angles_h, obs_h)
+    results = {}
+
+    def compute(local_particles, out_local):
+        rm.calc_range_repeat_angles_eval_sensor_model(local_particles, angles, obs, out_local)
+
+    upd = parallel.ShardedSensorUpdate(n_total, compute, device=dev)
+    w = upd.update(mine)
+    torch.cuda.synchronize()
+    results["nccl"] = np.array_equal(w.cpu().numpy().view(np.uint64), ref.view(np.uint64))
+    try:
+        peer = parallel.PeerStoreSensorUpdate(n_total, rm, angles, obs, device=dev)
+        w2 = peer.update(mine)
+        torch.cuda.synchronize()
+        results["peer"] = np.array_equal(w2.cpu().numpy().view(np.uint64), ref.view(np.uint64))
+    except Exception as ex:  # noqa: BLE001
+        results["peer"] = "unavailable: %s" % str(ex).splitlines()[0]
+    print("rank %d/%d: %s" % (rank, world, results), flush=True)
+    ok = results["nccl"] is True and results["peer"] in (True,) or isinstance(results["peer"], str)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
