@@ -276,3 +276,47 @@ def test_cython_drop_in_module():
     c.calc_range_many(qw, out)
     o = port.Oracle(port.PCDDT, occ, MR, TD)
     assert_bit_equal(out, o.numpy_calc_range(qw), "pcddt via range_libc")
+
+
+@pytest.mark.parametrize("name", ["huge_map", "gigantic_map"])
+def test_big_maps_against_digests(name):
+    """BASELINE config 3 sizes (10976^2, 4128x10976: sides > 4096, where the reference's distance transform
+    is no longer the exact EDT): device-built distance transform, CDDT and PCDDT tables and ranges against the
+    oracle's sha256 digests (tests/golden/big_digests.json, made by tests/golden/make_golden_big.py)."""
+    import hashlib
+    import json
+    import os
+    from helpers import GOLD
+    dig = json.load(open(os.path.join(GOLD, "big_digests.json")))[name]
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    occ = wl.load_map(name)
+    W, H = occ.shape
+    assert (W, H) == (dig["width"], dig["height"])
+    q = wl.random_queries(W, H, 20000, seed=777)
+    out = np.empty(len(q), np.float32)
+    rm = make("rm", occ)
+    assert sha(rm.distance_transform()) == dig["dt_sha256"]
+    rm.calc_range_many_grid(q, out)
+    assert sha(out) == dig["rm_ranges_sha256"]
+    del rm
+    bl = make("bl", occ)
+    bl.calc_range_many_grid(q, out)
+    assert sha(out) == dig["bl_ranges_sha256"]
+    del bl
+    cd = make("cddt", occ)
+    widths, trans, offsets, values = cd.table()
+    assert len(values) == dig["cddt_nvalues"]
+    assert sha(offsets) == dig["cddt_offsets_sha256"]
+    assert sha(values) == dig["cddt_values_sha256"]
+    cd.calc_range_many_grid(q, out)
+    assert sha(out) == dig["cddt_ranges_sha256"]
+    cd.prune()
+    widths, trans, offsets, values = cd.table()
+    assert len(values) == dig["pcddt_nvalues"]
+    assert sha(offsets) == dig["pcddt_offsets_sha256"]
+    assert sha(values) == dig["pcddt_values_sha256"]
+    cd.calc_range_many_grid(q, out)
+    assert sha(out) == dig["pcddt_ranges_sha256"]
