@@ -299,6 +299,17 @@ static float bl_calc_range(const orc_ctx* c, float x, float y, float heading) {
       _y += (float)ystep;
       error -= deltax;
     }
+    /* TERMINATION GUARD (not in the reference).  `_x += xstep` is a float accumulation: when _x crosses a
+     * power of two with low fraction bits set the sum rounds, (int)_x can jump over `target`, and the
+     * reference then walks on for ever (e.g. x=1188.2903 y=547.99994 heading=1.2550871 on the 1200^2 map).
+     * _x and _y move monotonically, so once a coordinate has left the map on the side it is moving
+     * towards no cell can be hit any more: whenever the reference terminates from here it returns
+     * max_range, so returning it now changes no result and only ends the walks the reference never ends. */
+    {
+      float lim_x = steep ? width : height, lim_y = steep ? height : width;
+      if ((xstep > 0) ? (_x >= lim_x) : (_x < 0.0f)) return c->max_range;
+      if ((ystep > 0) ? (_y >= lim_y) : (_y < 0.0f)) return c->max_range;
+    }
     if (!steep) {
       if (0 <= _y && _y < width && 0 <= _x && _x < height && occ_at(c, (int)_y, (int)_x)) {
         float xd = _x - x0, yd = _y - y0;

@@ -234,6 +234,7 @@ static void free_method(rl_method* m) {
   cddt_free(m);
   cudaFree(m->d_occ);
   cudaFree(m->d_bits_y);
+  cudaFree(m->d_bits_x);
   cudaFree(m->d_dt);
   cudaFree(m->d_table);
   cudaFree(m->d_stage);
@@ -436,7 +437,7 @@ int rl_debug_set_persistent(rl_method* m, int on) {
 
 int64_t rl_method_memory(const rl_method* m) {
   if (!m) return RL_E_INVALID;
-  int64_t bytes = (int64_t)m->W * m->H + (int64_t)m->W * m->wpy * 4;
+  int64_t bytes = (int64_t)m->W * m->H + (int64_t)m->W * m->wpy * 4 + (int64_t)m->H * m->wpx * 4;
   if (m->kind == RL_RM) bytes += (int64_t)m->dt_elems() * 4;
   if (m->kind >= RL_CDDT) bytes += m->nvalues * 4 + (m->nbins + 1) * 8 + (int64_t)m->td * 16;
   return bytes;

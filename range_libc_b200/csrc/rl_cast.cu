@@ -163,47 +163,111 @@ __device__ __forceinline__ bool occ_at(const MapView& mv, int x, int y) {  // OM
 }
 
 // BresenhamsLine::calc_range, RangeLib.h:696-769.  All state is float, as in the reference; the
-// walk is the reference's recurrence (_x += +-1, error += deltay) step for step.
-__device__ __forceinline__ float bl_cast(const MapView& mv, float max_range, float x, float y, float heading) {
-  if (!finite3(x, y, heading)) return max_range;  // the reference does not terminate on these
-  if (occ_at(mv, f2i(x), f2i(y))) return 0.0f;
+// walk is the reference's recurrence (_x += +-1, error += deltay, conditional _y += +-1) step for
+// step, so the visited cells and the returned distance are bit-identical.  What differs is how a
+// step is evaluated:
+//  * cell test = one bit of a register-cached 32-cell word.  The grid is kept bit-packed along BOTH
+//    axes; a ray reads the copy packed along its major axis, so 32 consecutive steps share one
+//    word and a new word is loaded only when the minor coordinate changes or the word is used up
+//    (~270 cell tests per ray cost ~15 loads);
+//  * the float bounds tests `0 <= v && v < limit` (:755/:761) become one unsigned compare of
+//    floor(v) -- identical for every finite v -- and floor(v) is also the cell index;
+//  * the loop test `(int)_x != (int)(x1 + xstep)` becomes an interval test on _x (trunc(v) == T is an
+//    interval of v), no conversion;
+//  * the reference keeps walking after the ray has left the map; coordinates are monotone along
+//    the walk, so once a coordinate has left on the side it is moving towards no cell can be hit
+//    any more and the result (max_range) is returned at once.
+struct BlState {
+  float _x, _y, error, deltax, deltay, xstep, ystep, lo, hi, x0, y0;
+  int cur_wi;
+  uint32_t cur;
+  int guard;
+  bool steep;
+};
+
+// everything before the walk (:698-745).  Returns true when the result is already known.
+__device__ __forceinline__ bool bl_setup(const MapView& mv, float max_range, float x, float y, float heading,
+                                         BlState& st, float* result) {
+  *result = max_range;
+  if (!finite3(x, y, heading)) return true;  // the reference does not terminate on these
+  if (occ_at(mv, f2i(x), f2i(y))) {
+    *result = 0.0f;
+    return true;
+  }
   float sn, cs;
   rl_sincosf(heading, &sn, &cs);
   float x0 = y, y0 = x;
   float x1 = fadd(y, fmul(max_range, sn));
   float y1 = fadd(x, fmul(max_range, cs));
-  const bool steep = fabsf(fsub(y1, y0)) > fabsf(fsub(x1, x0));
-  if (steep) {
+  st.steep = fabsf(fsub(y1, y0)) > fabsf(fsub(x1, x0));
+  if (st.steep) {
     float tmp = x0; x0 = y0; y0 = tmp;
     tmp = x1; x1 = y1; y1 = tmp;
   }
-  const float deltax = fabsf(fsub(x1, x0)), deltay = fabsf(fsub(y1, y0));
-  float error = 0.0f, _x = x0, _y = y0;
-  const float xstep = (x0 < x1) ? 1.0f : -1.0f;
-  const float ystep = (y0 < y1) ? 1.0f : -1.0f;
-  const int target = f2i(fadd(x1, xstep));
-  // bounds of the float-vs-unsigned compares at :755/:761: not steep -> _y < width, _x < height
-  const float lim_y = steep ? (float)(unsigned)mv.H : (float)(unsigned)mv.W;
-  const float lim_x = steep ? (float)(unsigned)mv.W : (float)(unsigned)mv.H;
-  int guard = f2i(max_range) + 16;  // the walk needs at most deltax + 3 steps
-  while (f2i(_x) != target) {
-    if (--guard < 0) break;
-    _x = fadd(_x, xstep);
-    error = fadd(error, deltay);
-    if (fmul(error, 2.0f) >= deltax) {  // (double)error*2.0 >= (double)deltax: doubling is exact
-      _y = fadd(_y, ystep);
-      error = fsub(error, deltax);
-    }
-    if (0.0f <= _y && _y < lim_y && 0.0f <= _x && _x < lim_x) {
-      int cx = steep ? __float2int_rz(_x) : __float2int_rz(_y);
-      int cy = steep ? __float2int_rz(_y) : __float2int_rz(_x);
-      if (occ_at(mv, cx, cy)) {
-        float xd = fsub(_x, x0), yd = fsub(_y, y0);
-        return __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
-      }
-    }
+  st.deltax = fabsf(fsub(x1, x0));
+  st.deltay = fabsf(fsub(y1, y0));
+  st.error = 0.0f;
+  st._x = st.x0 = x0;
+  st._y = st.y0 = y0;
+  st.xstep = (x0 < x1) ? 1.0f : -1.0f;
+  st.ystep = (y0 < y1) ? 1.0f : -1.0f;
+  // the loop ends when trunc(_x) == target, i.e. lo <= _x < hi
+  const int target = f2i(fadd(x1, st.xstep));
+  if (target > 0) { st.lo = (float)target; st.hi = (float)target + 1.0f; }
+  else if (target < 0) { st.lo = nextafterf((float)target - 1.0f, 0.0f); st.hi = nextafterf((float)target, 0.0f); }
+  else { st.lo = nextafterf(-1.0f, 0.0f); st.hi = 1.0f; }
+  if (target == INT_MIN || fabsf(x0) > 8388608.0f || fabsf(x1) > 8388608.0f) return true;  // far outside any map
+  st.cur_wi = -1;
+  st.cur = 0;
+  // Normally the walk takes deltax + 1..3 steps.  The reference's `_x += xstep` is a float accumulation:
+  // when _x crosses a power of two with low fraction bits set, the sum rounds and (int)_x can jump over
+  // the target, after which the reference keeps walking (and hangs once the walk is outside the map).
+  // We follow it for as long as a cell can still be hit; the "left the map for good" test in bl_step
+  // ends such walks with max_range.  The counter is only a backstop.
+  st.guard = f2i(max_range) + mv.W + mv.H + 16;
+  return st._x >= st.lo && st._x < st.hi;  // zero-length walk
+}
+
+// one iteration of the walk (:745-767).  Returns true when the ray has ended.
+__device__ __forceinline__ bool bl_step(const MapView& mv, float max_range, BlState& st, float* result) {
+  *result = max_range;
+  if (--st.guard < 0) return true;
+  st._x = fadd(st._x, st.xstep);
+  st.error = fadd(st.error, st.deltay);
+  if (fmul(st.error, 2.0f) >= st.deltax) {  // (double)error*2.0 >= (double)deltax: doubling is exact
+    st._y = fadd(st._y, st.ystep);
+    st.error = fsub(st.error, st.deltax);
   }
-  return max_range;
+  // not steep: _y indexes map x (< width), _x indexes map y (< height); steep: the other way round (:755/:761)
+  const unsigned lim_a = st.steep ? (unsigned)mv.W : (unsigned)mv.H;  // major coordinate _x
+  const unsigned lim_b = st.steep ? (unsigned)mv.H : (unsigned)mv.W;  // minor coordinate _y
+  const int a = __float2int_rd(st._x), b = __float2int_rd(st._y);
+  if ((unsigned)a < lim_a && (unsigned)b < lim_b) {
+    const int wi = b * (st.steep ? mv.wpx : mv.wpy) + (a >> 5);
+    if (wi != st.cur_wi) {
+      st.cur_wi = wi;
+      st.cur = __ldg((st.steep ? mv.bits_x : mv.bits_y) + wi);  // the copy packed along the major axis
+    }
+    if ((st.cur >> (a & 31)) & 1u) {
+      const float xd = fsub(st._x, st.x0), yd = fsub(st._y, st.y0);
+      *result = __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
+      return true;
+    }
+  } else {
+    // left the map on the side the walk is heading to: nothing can be hit any more
+    if ((st.xstep > 0.0f) ? (a >= (int)lim_a) : (a < 0)) return true;
+    if ((st.ystep > 0.0f) ? (b >= (int)lim_b) : (b < 0)) return true;
+  }
+  return st._x >= st.lo && st._x < st.hi;
+}
+
+__device__ __forceinline__ float bl_cast(const MapView& mv, float max_range, float x, float y, float heading) {
+  BlState st;
+  float result;
+  if (bl_setup(mv, max_range, x, y, heading, st, &result)) return result;
+  while (!bl_step(mv, max_range, st, &result)) {
+  }
+  return result;
 }
 
 // CDDTCast::discretize_theta RangeLib.h:1287-1340 (_USE_ALTERNATE_MOD 1, _USE_CACHED_CONSTANTS 1,
@@ -258,38 +322,38 @@ __device__ __forceinline__ float cddt_cast(const MapView& mv, const CddtView& cv
   const int high = size - 1;
   if (high == -1) return max_range;
   const float first = __ldg(B), last = __ldg(B + high);
+  // The reference scans bins of <= 65 entries linearly and uses std::upper_bound on larger ones.  A
+  // sorted, duplicate-free bin makes the linear scans equal to a binary search (first element >= lx,
+  // resp. last element <= lx), so every case below is one branch-free binary search; `strict` selects
+  // upper_bound (first element > lx) or lower_bound (first element >= lx).
   if (flipped) {
     if (first > lx) return max_range;
     if (last < lx) return fsub(lx, last);
     if (occ_at(mv, f2i(x), f2i(y))) return 0.0f;  // map.grid[x][y] :1413
-    if (high > RL_BINARY_SEARCH_THRESHOLD) {      // std::upper_bound: first element > lx
-      int lo = 0, hi = size;
-      while (lo < hi) {
-        int mid = lo + ((hi - lo) >> 1);
-        if (!(lx < __ldg(B + mid))) lo = mid + 1; else hi = mid;
-      }
-      return fsub(lx, __ldg(B + lo - 1));
+    // :1416-1418 upper_bound - 1; :1429-1443 last element <= lx == upper_bound - 1
+    int lo = 0, n = size;
+    while (n > 0) {
+      const int half = n >> 1;
+      const bool go_right = !(lx < __ldg(B + lo + half));
+      lo = go_right ? lo + half + 1 : lo;
+      n = go_right ? n - half - 1 : half;
     }
-    for (int i = high; i >= 0; --i) {
-      float v = __ldg(B + i);
-      if (v <= lx) return fsub(lx, v);
-    }
+    return fsub(lx, __ldg(B + lo - 1));
   } else {
     if (last < lx) return max_range;
     if (first > lx) return fsub(first, lx);
     if (occ_at(mv, f2i(x), f2i(y))) return 0.0f;  // :1475
-    if (high > RL_BINARY_SEARCH_THRESHOLD) {
-      int lo = 0, hi = size;
-      while (lo < hi) {
-        int mid = lo + ((hi - lo) >> 1);
-        if (!(lx < __ldg(B + mid))) lo = mid + 1; else hi = mid;
-      }
-      return fsub(__ldg(B + lo), lx);  // values[] is padded by one float: lo == size reads the pad
+    // :1480-1481 upper_bound (first > lx) for large bins; :1494-1510 first element >= lx for small ones
+    const bool strict = high > RL_BINARY_SEARCH_THRESHOLD;
+    int lo = 0, n = size;
+    while (n > 0) {
+      const int half = n >> 1;
+      const float v = __ldg(B + lo + half);
+      const bool go_right = strict ? !(lx < v) : (v < lx);
+      lo = go_right ? lo + half + 1 : lo;
+      n = go_right ? n - half - 1 : half;
     }
-    for (int i = 0; i < size; ++i) {
-      float v = __ldg(B + i);
-      if (v >= lx) return fsub(v, lx);
-    }
+    return fsub(__ldg(B + lo), lx);  // values[] is padded by one float: lo == size reads the pad
   }
   return -1.0f;  // the reference's assert(0) fall-through (:1514)
 }

@@ -61,6 +61,8 @@ struct MapView {
   const uint8_t* occ;      // x-major bytes occ[x*H+y]
   const uint32_t* bits_y;  // bit grid packed along y: word (x, y>>5), bit y&31; row stride wpy words
   int wpy;
+  const uint32_t* bits_x;  // the same grid packed along x: word (y, x>>5), bit x&31; row stride wpx words
+  int wpx;
   const float* dt;         // tiled float distance transform (RM), see dt_tiled_index
   int dt_tiles_y;
   int coop_threshold;      // RM: warps with at most this many live rays finish them cooperatively (0 = off)
@@ -118,6 +120,8 @@ struct rl_method {
   uint8_t* d_occ = nullptr;
   uint32_t* d_bits_y = nullptr;
   int wpy = 0;
+  uint32_t* d_bits_x = nullptr;
+  int wpx = 0;
   // RM
   float* d_dt = nullptr;
   // CDDT
@@ -146,7 +150,7 @@ struct rl_method {
   size_t dt_elems() const { return (size_t)dt_tiles_x() * dt_tiles_y() * 32; }
   int coop_threshold = 3;
   int persist = 1;  // RM large batches: 0 one ray per thread, 1 persistent warps with lane re-queuing
-  rl::MapView map_view() const { return rl::MapView{W, H, d_occ, d_bits_y, wpy, d_dt, dt_tiles_y(), coop_threshold}; }
+  rl::MapView map_view() const { return rl::MapView{W, H, d_occ, d_bits_y, wpy, d_bits_x, wpx, d_dt, dt_tiles_y(), coop_threshold}; }
   rl::CddtView cddt_view() const {
     return rl::CddtView{td, d_widths, d_trans, d_cosv, d_sinv, d_slice0, d_offsets, d_values, td_div_2pi, twopi_div_td};
   }

@@ -26,6 +26,27 @@ __global__ void pack_bits_kernel(const uint8_t* __restrict__ occ, uint32_t* __re
   bits[(size_t)x * wpy + wd] = v;
 }
 
+// x-packed copy: one thread per output word (y, x>>5)
+__global__ void pack_bits_x_kernel(const uint8_t* __restrict__ occ, uint32_t* __restrict__ bits, int W, int H, int wpx,
+                                   int y_begin, int y_end, int word_begin, int word_end) {
+  const int nw = word_end - word_begin;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)(y_end - y_begin) * nw;
+  if (idx >= total) return;
+  // consecutive threads take consecutive y so the byte reads of a warp are contiguous
+  const int ny = y_end - y_begin;
+  const int y = y_begin + (int)(idx % ny);
+  const int wd = word_begin + (int)(idx / ny);
+  const int x0 = wd << 5;
+  uint32_t v = 0;
+#pragma unroll 4
+  for (int b = 0; b < 32; ++b) {
+    int x = x0 + b;
+    if (x < W && occ[(size_t)x * H + y]) v |= (1u << b);
+  }
+  bits[(size_t)y * wpx + wd] = v;
+}
+
 __global__ void patch_kernel(uint8_t* __restrict__ occ, const uint8_t* __restrict__ patch, int H, int x0, int y0, int w,
                              int h) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -38,13 +59,22 @@ int upload_occupancy(rl_method* m, const rl_map* map) {
   const size_t n = (size_t)m->W * m->H;
   m->wpy = (m->H + 31) / 32;
   RL_CUDA(cudaMalloc(&m->d_occ, n ? n : 1));
+  m->wpx = (m->W + 31) / 32;
   RL_CUDA(cudaMalloc(&m->d_bits_y, sizeof(uint32_t) * (size_t)m->W * m->wpy + 4));
+  RL_CUDA(cudaMalloc(&m->d_bits_x, sizeof(uint32_t) * (size_t)m->H * m->wpx + 4));
   RL_CUDA(cudaMemcpyAsync(m->d_occ, map->occ.data(), n, cudaMemcpyHostToDevice, m->stream));
   const long long total = (long long)m->W * m->wpy;
   pack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_y, m->W, m->H, m->wpy, 0,
                                                                           m->W, 0, m->wpy);
   count_launch();
   RL_CHECK_LAUNCH();
+  const long long total_x = (long long)m->H * m->wpx;
+  if (total_x > 0) {
+    pack_bits_x_kernel<<<(unsigned)((total_x + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_x, m->W, m->H,
+                                                                               m->wpx, 0, m->H, 0, m->wpx);
+    count_launch();
+    RL_CHECK_LAUNCH();
+  }
   return RL_OK;
 }
 
@@ -56,6 +86,12 @@ int apply_patch(rl_method* m, const uint8_t* d_patch, int x0, int y0, int w, int
   const long long total = (long long)w * (we - wb);
   pack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_y, m->W, m->H, m->wpy,
                                                                           x0, x0 + w, wb, we);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  const int xb = x0 >> 5, xe = ((x0 + w - 1) >> 5) + 1;
+  const long long total_x = (long long)h * (xe - xb);
+  pack_bits_x_kernel<<<(unsigned)((total_x + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_x, m->W, m->H, m->wpx,
+                                                                             y0, y0 + h, xb, xe);
   count_launch();
   RL_CHECK_LAUNCH();
   return RL_OK;

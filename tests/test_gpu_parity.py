@@ -320,3 +320,25 @@ def test_big_maps_against_digests(name):
     assert sha(values) == dig["pcddt_values_sha256"]
     cd.calc_range_many_grid(q, out)
     assert sha(out) == dig["pcddt_ranges_sha256"]
+
+
+def test_bl_large_batches_and_reference_nontermination():
+    """Large BL batches incl. rays that start outside the map, and the ray on which the reference's float
+    `_x += xstep` accumulation jumps over its loop target (the reference never returns for it; oracle and
+    device both end the walk when it has left the map for good)."""
+    occ = wl.load_map("basement_hallways_5cm")
+    W, H = occ.shape
+    world = (0.05, 0.0, -30.0, -30.0, 0.0, 1.0)
+    meth = make("bl", occ, world=world)
+    o = port.Oracle(port.BL, occ, MR, threads=8)
+    o.set_world(*world)
+    n = 400_003
+    q = wl.random_queries(W, H, n, seed=41)
+    assert abs(q[101113, 0] - 1188.2903) < 1e-3  # the non-terminating ray is part of this batch
+    q[:64, 0] = np.linspace(-20, W + 20, 64)  # a few rays that start outside the map
+    out = np.empty(n, np.float32)
+    meth.calc_range_many_grid(q, out)
+    assert_bit_equal(out, o.calc_range_many(q), "grid")
+    qw = wl.grid_to_world(q, world[0], world[2], world[3])
+    meth.calc_range_many(qw, out)
+    assert_bit_equal(out, o.numpy_calc_range(qw), "world")
