@@ -51,8 +51,8 @@ __device__ __forceinline__ bool rm_step(const MapView& mv, float max_range, floa
 // 150-300 steps holds its warp -- and, in a small launch such as a 4000 x 60 particle-filter
 // update, the whole kernel -- for 30-60 us while 31 lanes idle.  Here the idle lanes turn the
 // chain into batches: the ray is a straight line, so the cells it can visit over the next
-// ~23 px are known before any distance is.  Lane j reads the distance at parameter
-// t + 0.75 j (one L2 round trip for all 32); the warp then replays the reference's stepping
+// ~48 px are known before any distance is.  Every lane reads the distance at two parameters
+// t + 0.75 (32 p + j) (one L2 round trip for all 64 probes); the warp then replays the reference's stepping
 // sequence out of registers, finding the cell of each exact sample position
 // (px, py) = (int)(x0 + dx t), (int)(y0 + dy t) among the lanes with a ballot.  A sample whose
 // cell was not prefetched (a corner clipped between two probes, or a jump past the window) just
@@ -60,45 +60,60 @@ __device__ __forceinline__ bool rm_step(const MapView& mv, float max_range, floa
 // advances at least one step.  Arithmetic and step sequence are the reference's, untouched:
 // the probes are a register-resident cache, never a source of different values.
 #define RL_COOP_SPACING 0.75f
-#define RL_STEP_HIT 0x7f800000u  // +inf: "this cell is an obstacle" in the per-lane step table
+#define RL_COOP_PROBES 2         // probes per lane and batch: 64 probes = 48 px of ray per L2 round trip
+#define RL_STEP_INF 0x7f800000u  // +inf in the per-lane step table: "obstacle here" -- and the value of "no probe"
 __device__ __forceinline__ float rm_march_coop(const MapView& mv, float max_range, float x0, float y0, float dx,
                                                float dy, float t) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned W = (unsigned)mv.W, H = (unsigned)mv.H;
   while (true) {
-    // ---- probe batch: lane j reads the cell at parameter t + 0.75 j and keeps the step it implies ----
-    const float s = t + (float)lane * RL_COOP_SPACING;  // lane 0: exactly t
-    const int cx = __float2int_rz(fadd(x0, fmul(dx, s)));
-    const int cy = __float2int_rz(fadd(y0, fmul(dy, s)));
-    int key = -1;
-    unsigned stepbits = 0u;
-    if ((unsigned)cx < W && (unsigned)cy < H) {
-      key = (cx << 16) | cy;  // map sides are < 32768 when this path is enabled
-      const float d = __ldg(mv.dt + dt_tiled_index(cx, cy, mv.dt_tiles_y));
-      stepbits = (d <= 0.0f) ? RL_STEP_HIT : __float_as_uint(fmaxf(fmul(d, 0.999f), 1.0f));
+    // ---- probe batch: probe p of lane j reads the cell at parameter t + 0.75 (32 p + j) and keeps the
+    // step that cell implies.  The loads of a lane are independent (one L2 round trip for the batch).
+    // Cells are identified by key = cx << 16 | cy; this path is only taken when W, H and max_range are
+    // below 32768, so a sample outside the map (coordinate negative or >= the side) can never produce
+    // the key of a probed cell; unused probes carry key -1 and a step of +inf.
+    int key[RL_COOP_PROBES];
+    unsigned stepbits[RL_COOP_PROBES];
+#pragma unroll
+    for (int p = 0; p < RL_COOP_PROBES; ++p) {
+      const float s = t + (float)(32 * p + lane) * RL_COOP_SPACING;  // p = 0, lane 0: exactly t
+      const int cx = __float2int_rz(fadd(x0, fmul(dx, s)));
+      const int cy = __float2int_rz(fadd(y0, fmul(dy, s)));
+      key[p] = -1;
+      stepbits[p] = RL_STEP_INF;
+      if ((unsigned)cx < W && (unsigned)cy < H) {
+        key[p] = (cx << 16) | cy;
+        const float d = __ldg(mv.dt + dt_tiled_index(cx, cy, mv.dt_tiles_y));
+        stepbits[p] = (d <= 0.0f) ? RL_STEP_INF : __float_as_uint(fmaxf(fmul(d, 0.999f), 1.0f));
+      }
     }
-    // ---- replay the reference's steps out of the probes: one warp-wide max-reduction per step.
-    // The loop has a single exit test; a sample whose cell was not probed, a sample outside the map and
-    // an obstacle all add +inf to t and are told apart afterwards.
+    // ---- replay the reference's steps out of the probes: one warp-wide min-reduction per step.
+    // A lane offers the step of its probe if the probe is the sampled cell, +inf otherwise; +inf
+    // (obstacle, cell not probed, or sample outside the map) ends the loop through its only exit
+    // test and the three cases are told apart afterwards.
     float tp;
-    unsigned r;
-    int px, py;
+    int k0, px, py;
     do {
       tp = t;
       px = __float2int_rz(fadd(x0, fmul(dx, t)));
       py = __float2int_rz(fadd(y0, fmul(dy, t)));
-      const int k0 = ((unsigned)px < W && (unsigned)py < H) ? ((px << 16) | py) : -2;
-      r = __reduce_max_sync(FULL, key == k0 ? stepbits : 0u);
-      t = fadd(t, __uint_as_float(r ? r : RL_STEP_HIT));
+      k0 = (px << 16) | py;
+      unsigned mine = (key[0] == k0) ? stepbits[0] : RL_STEP_INF;
+#pragma unroll
+      for (int p = 1; p < RL_COOP_PROBES; ++p) mine = (key[p] == k0) ? stepbits[p] : mine;
+      t = fadd(t, __uint_as_float(__reduce_min_sync(FULL, mine)));
     } while (t < max_range);
     if ((unsigned)px >= W || (unsigned)py >= H) return max_range;  // left the map (RangeLib.h:942-944)
-    if (r == RL_STEP_HIT) {                                        // d <= distThreshold (:952-956)
+    if (t != __uint_as_float(RL_STEP_INF)) return max_range;       // a real step carried t to max_range (:938)
+    bool probed = false;
+#pragma unroll
+    for (int p = 0; p < RL_COOP_PROBES; ++p) probed = probed || key[p] == k0;
+    if (__any_sync(FULL, probed)) {  // probed and +inf: d <= distThreshold (:952-956)
       const float xd = fsub((float)px, x0), yd = fsub((float)py, y0);
       return __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
     }
-    if (r != 0u) return max_range;  // a real step carried t to max_range (:938)
-    t = tp;                         // cell not probed: next batch starts at this sample
+    t = tp;  // cell not probed: next batch starts at this sample
   }
 }
 
@@ -112,7 +127,7 @@ __device__ __forceinline__ float rm_march_warp(const MapView& mv, float max_rang
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   float t = 0.0f, result = max_range;
-  const int coop = (mv.W < 32768 && mv.H < 32768) ? mv.coop_threshold : 0;
+  const int coop = (mv.W < 32768 && mv.H < 32768 && max_range < 32768.0f) ? mv.coop_threshold : 0;
   while (true) {
     unsigned act = __ballot_sync(FULL, active);
     if (!act) break;
@@ -413,7 +428,7 @@ __device__ __forceinline__ void load_pose(const WorldXform& xf, const float* __r
 
 // one ray per thread, grid-stride; the loop is warp-uniform so that RM can march at warp level
 template <int KIND, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, KIND == RL_RM ? 7 : 4)
 cast_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float* __restrict__ ins,
             const float* __restrict__ angles, float* __restrict__ outs, long long total, int M) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -440,7 +455,7 @@ cast_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float
 // Beams are processed in chunks of at most `chunk` so shared memory stays bounded for any M.
 // smem: double vals[ppb * chunk].
 template <int KIND>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, KIND == RL_RM ? 7 : 4)
 fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_range, const float* __restrict__ ins,
              const float* __restrict__ angles, const float* __restrict__ obs, double* __restrict__ weights, int N,
              int M, int ppb, int chunk, PeerOut peers) {
