@@ -411,34 +411,125 @@ def main():
         dist.destroy_process_group()
 
 
+def _time_launches(fn, stream, iters=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)) * 1e-3
+
+
 def extra_throughput(rl, wl, occ, omap, dev, stream, peak):
-    """Secondary numbers (not the judged line): large-batch ray casts/s per method on device-resident random
-    queries (16 algorithmic B/ray), north_star's 50 G rays/s RM target."""
+    """Secondary numbers (not the judged line), one per BASELINE config, all device resident:
+    large-batch ray casts/s per method (16 algorithmic B/ray; north_star's 50 G rays/s RM target), CDDT/PCDDT
+    build + query on gigantic_map (C3), BL on a dynamic 4096^2 grid (C4), fused RM + sensor model for
+    1M particles x 1080 beams on an 8192^2 grid (C5, one GPU's worth)."""
     import torch
     out = {}
     W, H = occ.shape
     N = 1 << 24
     q = torch.from_numpy(wl.random_queries(W, H, N, seed=1)).to(dev)
     r = torch.empty(N, dtype=torch.float32, device=dev)
+
+    def pcddt():
+        m = rl.PyCDDTCast(omap, MAX_RANGE, 108)
+        m.prune()
+        return m
+
     for nm, ctor in (("rm", lambda: rl.PyRayMarchingGPU(omap, MAX_RANGE)), ("cddt", lambda: rl.PyCDDTCast(omap, MAX_RANGE, 108)),
-                     ("bl", lambda: rl.PyBresenhamsLine(omap, MAX_RANGE))):
-        m = ctor()
-        m.set_stream(stream.cuda_stream)
-        n = N if nm != "bl" else N // 4
-        for _ in range(3):
-            m.calc_range_many_grid(q[:n], r[:n])
-        ts = []
-        for _ in range(10):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            m.calc_range_many_grid(q[:n], r[:n])
-            b.record(stream)
-            b.synchronize()
-            ts.append(a.elapsed_time(b))
-        t = float(np.median(ts)) * 1e-3
-        out[nm + "_random_rays_per_s"] = n / t
-        out[nm + "_random_hbm_frac"] = 16.0 * n / t / 1e9 / peak
+                     ("pcddt", pcddt), ("bl", lambda: rl.PyBresenhamsLine(omap, MAX_RANGE))):
+        try:
+            m = ctor()
+            m.set_stream(stream.cuda_stream)
+            n = N if nm != "bl" else N // 4
+            t = _time_launches(lambda: m.calc_range_many_grid(q[:n], r[:n]), stream)
+            out[nm + "_random_rays_per_s"] = n / t
+            out[nm + "_random_hbm_frac"] = 16.0 * n / t / 1e9 / peak
+            del m
+        except Exception as ex:  # noqa: BLE001
+            out[nm + "_error"] = str(ex)[:200]
     out["workload"] = "2^24 uniformly random grid-coordinate queries on %s (BL: 2^22), max_range 500, device resident" % MAP
+    del q, r
+    # C3: CDDT / PCDDT on gigantic_map (10976^2), theta_discretization 108
+    try:
+        big = wl.load_map("gigantic_map")
+        bmap = rl.PyOMap(np.ascontiguousarray(big.T.astype(bool)))
+        t0 = time.perf_counter()
+        cd = rl.PyCDDTCast(bmap, MAX_RANGE, 108)
+        t_build = time.perf_counter() - t0
+        cd.set_stream(stream.cuda_stream)
+        n = 1 << 24
+        qb = torch.from_numpy(wl.random_queries(big.shape[0], big.shape[1], n, seed=2)).to(dev)
+        rb = torch.empty(n, dtype=torch.float32, device=dev)
+        t_q = _time_launches(lambda: cd.calc_range_many_grid(qb, rb), stream, iters=5)
+        t0 = time.perf_counter()
+        cd.prune()
+        t_prune = time.perf_counter() - t0
+        t_qp = _time_launches(lambda: cd.calc_range_many_grid(qb, rb), stream, iters=5)
+        out["c3_gigantic_map"] = {"cddt_build_s": t_build, "pcddt_prune_s": t_prune, "cddt_rays_per_s": n / t_q,
+                                  "pcddt_rays_per_s": n / t_qp, "table_bytes_after_prune": cd.memory(),
+                                  "note": "build/prune include upload of the 120 MB grid and all device work; CPU reference: "
+                                          "CDDT build ~15 s, prune ~24 min (SURVEY.md section 6)"}
+        del cd, qb, rb, bmap, big
+    except Exception as ex:  # noqa: BLE001
+        out["c3_error"] = str(ex)[:200]
+    # C4: Bresenham on a dynamic 4096^2 grid: per frame 64 16x16 occupancy patches + 2^20 rays
+    try:
+        occ4 = wl.synthetic_map(4096, seed=2026)
+        m4 = rl.PyOMap(np.ascontiguousarray(occ4.T.astype(bool)))
+        bl = rl.PyBresenhamsLine(m4, MAX_RANGE)
+        bl.set_stream(stream.cuda_stream)
+        n = 1 << 20
+        q4 = torch.from_numpy(wl.random_queries(4096, 4096, n, seed=3)).to(dev)
+        r4 = torch.empty(n, dtype=torch.float32, device=dev)
+        frames = [[(x0, y0, torch.from_numpy(p).to(dev)) for x0, y0, p in wl.flip_blocks(occ4, f, seed=2026)] for f in range(8)]
+
+        def frame(f):
+            for x0, y0, p in frames[f % 8]:
+                bl.update_map(p, x0, y0)
+            bl.calc_range_many_grid(q4, r4)
+
+        for f in range(3):
+            frame(f)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for f in range(16):
+            frame(f)
+        b.record(stream)
+        b.synchronize()
+        t = a.elapsed_time(b) * 1e-3 / 16
+        out["c4_dynamic_bl_4096"] = {"ms_per_frame": t * 1e3, "rays_per_s": n / t, "patches_per_frame": 64,
+                                     "note": "update + query per frame; the CPU reference copies the whole map per BresenhamsLine"}
+        del bl, q4, r4, m4
+    except Exception as ex:  # noqa: BLE001
+        out["c4_error"] = str(ex)[:200]
+    # C5: fused RM + sensor model, 1M particles x 1080 beams on a synthetic 8192^2 grid (single GPU share of the config)
+    try:
+        occ5 = wl.synthetic_map(8192, seed=2026)
+        m5 = rl.PyOMap(np.ascontiguousarray(occ5.T.astype(bool)))
+        t0 = time.perf_counter()
+        rm5 = rl.PyRayMarchingGPU(m5, MAX_RANGE)
+        t_dt = time.perf_counter() - t0
+        rm5.set_sensor_model(wl.sensor_table(K_TABLE))
+        rm5.set_stream(stream.cuda_stream)
+        n5, m_beams = 1_000_000, 1080
+        p5 = torch.from_numpy(wl.pf_particles_uniform(occ5, n5, seed=4)).to(dev)
+        a5 = torch.from_numpy(wl.lidar_angles(m_beams)).to(dev)
+        o5 = torch.from_numpy(np.clip(150 + 100 * np.sin(np.linspace(0, 6, m_beams)), 0, 500).astype(np.float32)).to(dev)
+        w5 = torch.empty(n5, dtype=torch.float64, device=dev)
+        t = _time_launches(lambda: rm5.calc_range_repeat_angles_eval_sensor_model(p5, a5, o5, w5), stream, iters=3, warm=1)
+        out["c5_rm_fused_8192"] = {"particles": n5, "beams": m_beams, "s_per_update": t, "rays_per_s": n5 * m_beams / t,
+                                   "dt_build_s": t_dt, "note": "268 MB distance transform (> L2): sector traffic is HBM traffic here"}
+        del rm5, p5, w5, m5
+    except Exception as ex:  # noqa: BLE001
+        out["c5_error"] = str(ex)[:200]
     return out
 
 

@@ -552,12 +552,8 @@ int rl_debug_get_dt(rl_method* m, float* out) {
     set_error("rl_debug_get_dt: not an RM method");
     return RL_E_STATE;
   }
-  std::vector<float> tiled(m->dt_elems());
-  RL_CUDA(cudaMemcpyAsync(tiled.data(), m->d_dt, sizeof(float) * tiled.size(), cudaMemcpyDeviceToHost, m->stream));
+  RL_CUDA(cudaMemcpyAsync(out, m->d_dt, sizeof(float) * m->dt_elems(), cudaMemcpyDeviceToHost, m->stream));
   RL_CUDA(cudaStreamSynchronize(m->stream));
-  const int ty = m->dt_tiles_y();
-  for (int x = 0; x < m->W; ++x)
-    for (int y = 0; y < m->H; ++y) out[(size_t)x * m->H + y] = tiled[dt_tiled_index(x, y, ty)];
   return RL_OK;
 }
 

@@ -27,14 +27,14 @@ __device__ __forceinline__ bool finite3(float a, float b, float c) {
 // ---- RayMarching::calc_range, RangeLib.h:927-962; distThreshold 0.0, step_coeff 0.999f (:967-968) ----
 //
 // rm_step: one iteration of the reference's while loop for one ray (one dependent read of the
-// tiled float distance transform).  Returns true when the ray has ended and `result` is final.
+// float distance transform).  Returns true when the ray has ended and `result` is final.
 __device__ __forceinline__ bool rm_step(const MapView& mv, float max_range, float x0, float y0, float dx, float dy,
                                         float& t, float& result) {
   const int px = __float2int_rz(fadd(x0, fmul(dx, t)));
   const int py = __float2int_rz(fadd(y0, fmul(dy, t)));
   result = max_range;
   if ((unsigned)px >= (unsigned)mv.W || (unsigned)py >= (unsigned)mv.H) return true;
-  const float d = __ldg(mv.dt + dt_tiled_index(px, py, mv.dt_tiles_y));
+  const float d = __ldg(mv.dt + dt_index(px, py, mv.H));
   if (d <= 0.0f) {
     const float xd = fsub((float)px, x0), yd = fsub((float)py, y0);
     result = __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
@@ -84,7 +84,7 @@ __device__ __forceinline__ float rm_march_coop(const MapView& mv, float max_rang
       stepbits[p] = RL_STEP_INF;
       if ((unsigned)cx < W && (unsigned)cy < H) {
         key[p] = (cx << 16) | cy;
-        const float d = __ldg(mv.dt + dt_tiled_index(cx, cy, mv.dt_tiles_y));
+        const float d = __ldg(mv.dt + dt_index(cx, cy, mv.H));
         stepbits[p] = (d <= 0.0f) ? RL_STEP_INF : __float_as_uint(fmaxf(fmul(d, 0.999f), 1.0f));
       }
     }
@@ -565,6 +565,9 @@ __global__ void sincosf_kernel(const float* x, float* s, float* c, int n) {
 // batches and the marching loop runs with ~all lanes busy until the chunk is exhausted.
 // ------------------------------------------------------------------------------------------
 #define RL_QB 4  // parked rays per lane and setup phase
+#ifndef RL_PERSIST_BURST
+#define RL_PERSIST_BURST 4
+#endif
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 6)
@@ -632,9 +635,14 @@ rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
     }
     if (!__any_sync(FULL, active)) break;
     if (active) {
-      // one iteration of RayMarching::calc_range's loop (RangeLib.h:938-959)
+      // a short burst of iterations of RayMarching::calc_range's loop (RangeLib.h:938-959) between two
+      // re-queuing rounds: the refill bookkeeping (~25 instructions) is paid once per burst
       float result;
-      const bool done = rm_step(mv, max_range, x0, y0, dx, dy, t, result);
+      bool done;
+      int burst = RL_PERSIST_BURST;
+      do {
+        done = rm_step(mv, max_range, x0, y0, dx, dy, t, result);
+      } while (!done && --burst);
       if (done) {
         outs[id] = (MODE == MODE_GRID) ? result : fmul(result, out_scale);
         active = false;

@@ -22,19 +22,18 @@ __device__ __forceinline__ float edt_load(const uint8_t* __restrict__ occ, const
   return fin[base + q * es];
 }
 
-// FINAL: second pass -- square-rooted and written in the tiled residency layout (line = y, q = x)
+// FINAL_SQRT: second pass -- square-rooted (line = y, q = x, written x-major)
 template <bool FROM_OCC, bool FINAL_SQRT>
 __global__ void __launch_bounds__(64)
 edt_pass_kernel(const uint8_t* __restrict__ occ, const float* __restrict__ fin, float* __restrict__ out, int nlines,
                 int n, long long in_ls, long long in_es, long long out_ls, long long out_es, int* __restrict__ vstk,
-                float* __restrict__ fstk, double* __restrict__ zstk, int tiles_y) {
+                float* __restrict__ fstk, double* __restrict__ zstk) {
   const int line = blockIdx.x * blockDim.x + threadIdx.x;
   if (line >= nlines) return;
   const long long ib = (long long)line * in_ls, ob = (long long)line * out_ls;
   if (n == 1) {  // distance_transform.h:1058-1062
     float v = edt_load<FROM_OCC>(occ, fin, ib, in_es, 0);
-    if (FINAL_SQRT) out[dt_tiled_index(0, line, tiles_y)] = __fsqrt_rn(v);
-    else out[ob] = v;
+    out[ob] = FINAL_SQRT ? __fsqrt_rn(v) : v;
     return;
   }
   // lower envelope (:1072-1083).  The top entry lives in registers; entries below it in scratch.
@@ -86,8 +85,7 @@ edt_pass_kernel(const uint8_t* __restrict__ occ, const float* __restrict__ fin, 
     }
     const float dq = fsub((float)q, (float)cur_v);
     const float D = fadd(cur_f, fmul(dq, dq));
-    if (FINAL_SQRT) out[dt_tiled_index(q, line, tiles_y)] = __fsqrt_rn(D);
-    else out[ob + q * out_es] = D;
+    out[ob + q * out_es] = FINAL_SQRT ? __fsqrt_rn(D) : D;
   }
 }
 
@@ -112,11 +110,11 @@ int build_distance_transform(rl_method* m) {
   const int threads = 64;
   // pass 1: for each x a scanline along y (slices of dimension 0 first, :893-900)
   edt_pass_kernel<true, false><<<(W + threads - 1) / threads, threads, 0, m->stream>>>(
-      m->d_occ, nullptr, d_tmp, W, H, (long long)H, 1LL, (long long)H, 1LL, vstk, fstk, zstk, m->dt_tiles_y());
+      m->d_occ, nullptr, d_tmp, W, H, (long long)H, 1LL, (long long)H, 1LL, vstk, fstk, zstk);
   count_launch();
   // pass 2: for each y a scanline along x; result square-rooted (:1117-1121)
   edt_pass_kernel<false, true><<<(H + threads - 1) / threads, threads, 0, m->stream>>>(
-      nullptr, d_tmp, m->d_dt, H, W, 1LL, (long long)H, 1LL, (long long)H, vstk, fstk, zstk, m->dt_tiles_y());
+      nullptr, d_tmp, m->d_dt, H, W, 1LL, (long long)H, 1LL, (long long)H, vstk, fstk, zstk);
   count_launch();
   cudaError_t e = cudaGetLastError();
   cudaError_t e2 = cudaStreamSynchronize(m->stream);

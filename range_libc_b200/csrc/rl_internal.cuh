@@ -40,19 +40,13 @@ struct WorldXform {
   float inv_scale, scale, ox, oy, sin_a, cos_a, rot;
 };
 
-// Distance-transform residency layout.  The grid is cut into tiles of 8 (x) by 4 (y) cells = 32
-// floats = one 128-byte L1/L2 line; inside a tile the cells are bit-interleaved so that each
-// 32-byte sector (the unit the L1 actually fills on a miss) covers a 4x2 block.  A ray that
-// creeps along a wall one pixel at a time therefore stays inside one sector / line for
-// several consecutive sphere-tracing steps whatever its direction, instead of touching a new
-// line on every step as it does in the reference's x-major vector<vector<float>>.
-#define RL_DT_TILE_X_SHIFT 3
-#define RL_DT_TILE_Y_SHIFT 2
-__host__ __device__ __forceinline__ unsigned dt_tiled_index(int px, int py, int tiles_y) {
-  const unsigned ux = (unsigned)px, uy = (unsigned)py;
-  const unsigned tile = (ux >> RL_DT_TILE_X_SHIFT) * (unsigned)tiles_y + (uy >> RL_DT_TILE_Y_SHIFT);
-  const unsigned low = (ux & 3u) | ((uy & 1u) << 2) | ((ux & 4u) << 1) | ((uy & 2u) << 3);
-  return (tile << 5) | low;
+// Distance-transform residency layout: plain x-major floats, dt[x*H + y], the order of the reference's
+// DistanceTransform::grid[x][y] (RangeLib.h:328).  A 128-byte-tile layout with bit-interleaved 4x2
+// sectors was built and measured in round 1: it costs ~8 more integer instructions per
+// sphere-tracing step and was 4-10 % SLOWER on every RM workload (the kernels are
+// instruction-issue / latency bound, not L1-hit bound; profiles/ab_dt_layout_r01.log), so it was removed.
+__host__ __device__ __forceinline__ unsigned dt_index(int px, int py, int H) {
+  return (unsigned)px * (unsigned)H + (unsigned)py;
 }
 
 // read-only view of the resident structures handed to kernels
@@ -63,8 +57,7 @@ struct MapView {
   int wpy;
   const uint32_t* bits_x;  // the same grid packed along x: word (y, x>>5), bit x&31; row stride wpx words
   int wpx;
-  const float* dt;         // tiled float distance transform (RM), see dt_tiled_index
-  int dt_tiles_y;
+  const float* dt;         // float distance transform (RM), x-major, see dt_index
   int coop_threshold;      // RM: warps with at most this many live rays finish them cooperatively (0 = off)
 };
 
@@ -145,12 +138,10 @@ struct rl_method {
   void* h_stage_dev = nullptr;  // its device alias (zero-copy)
   size_t h_stage_bytes = 0;
 
-  int dt_tiles_x() const { return (W + 7) >> 3; }
-  int dt_tiles_y() const { return (H + 3) >> 2; }
-  size_t dt_elems() const { return (size_t)dt_tiles_x() * dt_tiles_y() * 32; }
+  size_t dt_elems() const { return (size_t)W * H; }
   int coop_threshold = 3;
   int persist = 1;  // RM large batches: 0 one ray per thread, 1 persistent warps with lane re-queuing
-  rl::MapView map_view() const { return rl::MapView{W, H, d_occ, d_bits_y, wpy, d_bits_x, wpx, d_dt, dt_tiles_y(), coop_threshold}; }
+  rl::MapView map_view() const { return rl::MapView{W, H, d_occ, d_bits_y, wpy, d_bits_x, wpx, d_dt, coop_threshold}; }
   rl::CddtView cddt_view() const {
     return rl::CddtView{td, d_widths, d_trans, d_cosv, d_sinv, d_slice0, d_offsets, d_values, td_div_2pi, twopi_div_td};
   }
