@@ -232,24 +232,42 @@ def main():
     peer, gather_mode = None, "none (single GPU)"
     if world > 1:
         gather_mode = "nccl all_gather_into_tensor"
-        if os.environ.get("RL_BENCH_GATHER", "peer") == "peer":
+        # "peer" (fused peer stores + symmetric-memory barrier) measured 31.1 us/step at N=2 against 34.7 us for
+        # "signal" (one kernel per step with in-kernel epoch flags: every CTA pays a system-scope fence) when the
+        # steps are replayed from a CUDA graph; launched eagerly "signal" is the faster one (33.7 vs 36.0 us).
+        want = os.environ.get("RL_BENCH_GATHER", "peer")
+        if want in ("peer", "signal"):
             try:
                 from range_libc_b200 import parallel
-                peer = parallel.PeerStoreSensorUpdate(world * N_PART, rm, angles, obs, device=dev)
+                if want == "signal":
+                    peer = parallel.SignalledSensorUpdate(world * N_PART, rm, angles, obs, device=dev)
+                    gather_mode = ("one kernel per step: fused compute + peer stores over NVLink (symmetric memory, double "
+                                   "buffered) + in-kernel epoch flags; no barrier launch, no NCCL call")
+                else:
+                    peer = parallel.PeerStoreSensorUpdate(world * N_PART, rm, angles, obs, device=dev)
+                    gather_mode = "fused kernel epilogue: peer stores over NVLink into symmetric memory + symm barrier"
                 peer.update(set_views[0])
                 torch.cuda.synchronize()
-                gather_mode = "fused kernel epilogue: peer stores over NVLink into symmetric memory + symm barrier"
             except Exception as ex:  # noqa: BLE001
                 peer = None
                 gather_mode = "nccl all_gather_into_tensor (symmetric memory unavailable: %s)" % str(ex).splitlines()[0][:100]
+    signalled = peer is not None and hasattr(peer, "flags")
 
     def step(i):
         if peer is not None:
-            peer.update(set_views[i % n_sets])
+            if signalled:  # the next step's kernel waits in-kernel for this step's gather; see finish()
+                peer.update(set_views[i % n_sets], wait=False)
+            else:
+                peer.update(set_views[i % n_sets])
             return
         rm.calc_range_repeat_angles_eval_sensor_model(set_views[i % n_sets], angles, obs, my_w)
         if world > 1:
             dist.all_gather_into_tensor(weights_all, my_w)
+
+    def finish():
+        """close the last step: every rank's slice of the last gather has arrived (signalled mode)"""
+        if signalled:
+            rm.peers_wait()
 
     def barrier():
         if world > 1:
@@ -260,6 +278,7 @@ def main():
     sampler.start()
     for i in range(W_):
         step(i)
+    finish()
     barrier()
 
     # The K timed steps are captured once into a CUDA graph (launch-bound inner loop: each step is a
@@ -275,6 +294,7 @@ def main():
             rm.set_stream(torch.cuda.current_stream().cuda_stream)
             for i in range(K_):
                 step(W_ + i)
+            finish()
         rm.set_stream(stream.cuda_stream)
         graph.replay()  # untimed: instantiation / first-run costs
         barrier()
@@ -293,6 +313,7 @@ def main():
     else:
         for i in range(K_):
             step(W_ + i)
+        finish()
     e1.record(stream)
     barrier()
     launches = (rl.kernel_launches() - l0) if graph is None else K_
@@ -309,6 +330,7 @@ def main():
     e0.record(stream)
     for i in range(K_):
         step(W_ + i)
+    finish()
     e1.record(stream)
     barrier()
     eager_ms = e0.elapsed_time(e1) / K_

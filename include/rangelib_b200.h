@@ -129,6 +129,24 @@ int rl_calc_range_repeat_angles_eval_sensor_model_peers(rl_method* m, const floa
                                                         const float* obs, double* const* peer_weights, int n_peers,
                                                         int64_t offset, int num_particles, int num_angles);
 
+/* Signalled form: the same fused kernel also carries the synchronisation, so a step is ONE kernel per
+ * rank and nothing else (no barrier launch, no NCCL call).
+ *   rl_method_peers_init   weights0[r] / weights1[r]: rank r's two gathered weight arrays (double
+ *                          buffering), flags[r]: rank r's int64[n_peers] flag array (zero-initialised),
+ *                          all peer mapped; rank = this process.
+ *   ..._signalled          launch epoch e (1, 2, ... counted per handle; every rank must issue the same
+ *                          sequence): waits in-kernel until every rank has finished epoch e-1, stores this
+ *                          rank's weights into buffer e & 1 of every rank at `offset`, and the last CTA
+ *                          publishes flags[r][rank] = e everywhere.  *buffer_index = e & 1.
+ *   rl_method_peers_wait   enqueue a wait (on the handle's stream) until every rank's slice of the
+ *                          latest epoch has arrived; after it the gathered array may be read. */
+int rl_method_peers_init(rl_method* m, double* const* weights0, double* const* weights1, int64_t* const* flags,
+                         int n_peers, int rank);
+int rl_calc_range_repeat_angles_eval_sensor_model_signalled(rl_method* m, const float* ins, const float* angles,
+                                                            const float* obs, int64_t offset, int num_particles,
+                                                            int num_angles, int* buffer_index);
+int rl_method_peers_wait(rl_method* m);
+
 /* ---- table-level access for parity tests ---------------------------------------------------- */
 /* distance transform, x-major out[x*H+y] (DistanceTransform::grid RangeLib.h:328); RL_RM only. out: HOST */
 int rl_debug_get_dt(rl_method* m, float* out);

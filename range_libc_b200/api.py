@@ -168,6 +168,27 @@ class _RangeMethod:
         check(lib().rl_calc_range_repeat_angles_eval_sensor_model_peers(self._h, pi, pa, pb, arr, len(peer_ptrs),
                                                                         int(offset), si[0], sa[0]))
 
+    def peers_init(self, weights0_ptrs, weights1_ptrs, flags_ptrs, rank):
+        """Signalled multi-GPU mode: peer-mapped pointers of every rank's two weight buffers and flag array."""
+        n = len(weights0_ptrs)
+        mk = lambda ps: (C.c_void_p * n)(*[int(p) for p in ps])  # noqa: E731
+        check(lib().rl_method_peers_init(self._h, mk(weights0_ptrs), mk(weights1_ptrs), mk(flags_ptrs), n, int(rank)))
+
+    def calc_range_repeat_angles_eval_sensor_model_signalled(self, ins, angles, obs, offset):
+        """One kernel per rank: compute + peer-store all-gather + completion flags.  Returns the buffer index."""
+        pi, si = _buf(ins, np.float32, 2, "ins")
+        pa, sa = _buf(angles, np.float32, 1, "angles")
+        pb, sb = _buf(obs, np.float32, 1, "obs")
+        if si[1] != 3 or sb[0] < sa[0]:
+            raise ValueError("shape mismatch")
+        buf = C.c_int()
+        check(lib().rl_calc_range_repeat_angles_eval_sensor_model_signalled(self._h, pi, pa, pb, int(offset), si[0], sa[0],
+                                                                            C.byref(buf)))
+        return buf.value
+
+    def peers_wait(self):
+        check(lib().rl_method_peers_wait(self._h))
+
     def eval_sensor_model(self, observation, ranges, outs, num_rays, num_particles):
         pb, sb = _buf(observation, np.float32, 1, "observation")
         pr, sr = _buf(ranges, np.float32, 1, "ranges")

@@ -240,6 +240,8 @@ static void free_method(rl_method* m) {
   cudaFree(m->d_dt);
   cudaFree(m->d_table);
   cudaFree(m->d_stage);
+  cudaFree(m->d_epoch);
+  cudaFree(m->d_counter);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   if (m->ev) cudaEventDestroy(m->ev);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -528,7 +530,7 @@ int rl_calc_range_repeat_angles_eval_sensor_model_peers(rl_method* m, const floa
     set_error("the peer-store variant takes device pointers only");
     return RL_E_MIXED;
   }
-  PeerOut po;
+  PeerOut po{};
   po.n = n_peers;
   po.offset = offset;
   for (int r = 0; r < n_peers; ++r) {
@@ -543,6 +545,78 @@ int rl_calc_range_repeat_angles_eval_sensor_model_peers(rl_method* m, const floa
     return RL_E_INVALID;
   }
   return launch_cast(m, MODE_FUSED, ins, angles, obs, nullptr, nullptr, n, M, &po);
+}
+
+int rl_method_peers_init(rl_method* m, double* const* weights0, double* const* weights1, int64_t* const* flags,
+                         int n_peers, int rank) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (!weights0 || !weights1 || !flags || n_peers < 1 || n_peers > RL_MAX_PEERS || rank < 0 || rank >= n_peers) {
+    set_error("rl_method_peers_init: bad arguments");
+    return RL_E_INVALID;
+  }
+  if (!m->d_epoch) {
+    RL_CUDA(cudaMalloc(&m->d_epoch, sizeof(long long)));
+    RL_CUDA(cudaMalloc(&m->d_counter, sizeof(unsigned)));
+  }
+  RL_CUDA(cudaMemsetAsync(m->d_epoch, 0, sizeof(long long), m->stream));
+  RL_CUDA(cudaMemsetAsync(m->d_counter, 0, sizeof(unsigned), m->stream));
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  PeerOut& po = m->peer_cfg;
+  po = PeerOut{};
+  po.n = n_peers;
+  po.sig = 1;
+  po.rank = rank;
+  for (int r = 0; r < n_peers; ++r) {
+    if (!weights0[r] || !weights1[r] || !flags[r]) {
+      set_error("rl_method_peers_init: null peer pointer");
+      return RL_E_INVALID;
+    }
+    po.ptr[r] = weights0[r];
+    po.ptr1[r] = weights1[r];
+    po.flags[r] = (long long*)flags[r];
+  }
+  po.epoch = m->d_epoch;
+  po.counter = m->d_counter;
+  m->host_epoch = 0;
+  m->peers_ready = true;
+  return RL_OK;
+}
+
+int rl_calc_range_repeat_angles_eval_sensor_model_signalled(rl_method* m, const float* ins, const float* angles,
+                                                            const float* obs, int64_t offset, int n, int M,
+                                                            int* buffer_index) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (!m->peers_ready) {
+    set_error("rl_method_peers_init has not been called");
+    return RL_E_STATE;
+  }
+  if (n <= 0 || M <= 0 || offset < 0 || !ins || !angles || !obs) {
+    set_error("signalled fused call: bad arguments (every rank must launch with n > 0, num_angles > 0)");
+    return RL_E_INVALID;
+  }
+  if (!is_device_ptr(ins) || !is_device_ptr(angles) || !is_device_ptr(obs)) {
+    set_error("the signalled variant takes device pointers only");
+    return RL_E_MIXED;
+  }
+  PeerOut po = m->peer_cfg;
+  po.offset = offset;
+  rc = launch_cast(m, MODE_FUSED, ins, angles, obs, nullptr, nullptr, n, M, &po);
+  if (rc) return rc;
+  m->host_epoch += 1;
+  if (buffer_index) *buffer_index = (int)(m->host_epoch & 1);
+  return RL_OK;
+}
+
+int rl_method_peers_wait(rl_method* m) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (!m->peers_ready) {
+    set_error("rl_method_peers_init has not been called");
+    return RL_E_STATE;
+  }
+  return launch_peers_wait(m);
 }
 
 int rl_debug_get_dt(rl_method* m, float* out) {

@@ -462,6 +462,18 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
   extern __shared__ double vals[];
   const float kmax = (float)((double)(float)sv.K - 1.0);
   const int groups = (N + ppb - 1) / ppb;
+  long long epoch = 0;
+  if (peers.sig) {
+    // signalled multi-GPU mode: this launch is epoch e; wait until every rank has finished e-1
+    epoch = *(volatile long long*)peers.epoch + 1;
+    if (threadIdx.x < peers.n) {
+      volatile long long* mine = peers.flags[peers.rank];
+      while (mine[threadIdx.x] < epoch - 1) {
+      }
+    }
+    __syncthreads();
+  }
+  double* const* out_ptrs = (peers.sig && (epoch & 1)) ? peers.ptr1 : peers.ptr;
   for (int g = blockIdx.x; g < groups; g += gridDim.x) {
     const int p0 = g * ppb;
     const int np = min(ppb, N - p0);
@@ -509,8 +521,34 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
       if (peers.n == 0) {
         weights[p0 + threadIdx.x] = w;
       } else {  // all-gather by direct peer stores (NVLink): every GPU gets this rank's slice
-        for (int r = 0; r < peers.n; ++r) peers.ptr[r][peers.offset + p0 + threadIdx.x] = w;
+        for (int r = 0; r < peers.n; ++r) out_ptrs[r][peers.offset + p0 + threadIdx.x] = w;
       }
+    }
+  }
+  if (peers.sig) {
+    // publish: once every CTA of this launch has made its peer stores visible system-wide, the last one
+    // to arrive tells every rank that this rank's slice of epoch e is complete
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned done = atomicAdd(peers.counter, 1u);
+      if (done == gridDim.x - 1) {
+        *peers.counter = 0u;
+        __threadfence_system();
+        *(volatile long long*)peers.epoch = epoch;
+        for (int r = 0; r < peers.n; ++r) ((volatile long long*)peers.flags[r])[peers.rank] = epoch;
+      }
+    }
+  }
+}
+
+// consumer-side wait of the signalled mode: returns (on the stream) once every rank's slice of the
+// latest epoch launched on this rank has arrived
+__global__ void peers_wait_kernel(PeerOut peers) {
+  const long long epoch = *(volatile long long*)peers.epoch;
+  if (threadIdx.x < peers.n) {
+    volatile long long* mine = peers.flags[peers.rank];
+    while (mine[threadIdx.x] < epoch) {
     }
   }
 }
@@ -681,9 +719,7 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     const int groups = (n + ppb - 1) / ppb;
     const int grid = max(1, min(groups, sm_count() * 8));
     const size_t smem = (size_t)ppb * chunk * sizeof(double);
-    PeerOut po;
-    po.n = 0;
-    po.offset = 0;
+    PeerOut po{};
     if (peers) po = *peers;
     fused_kernel<KIND><<<grid, threads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range, ins, angles,
                                                            obs, weights, n, M, ppb, chunk, po);
@@ -745,6 +781,13 @@ int launch_eval_sensor(rl_method* m, const float* obs, const float* ranges, doub
   const size_t smem = (size_t)ppb * chunk * sizeof(double);
   eval_sensor_kernel<<<grid, threads, smem, m->stream>>>(m->sensor_view(), m->xf.inv_scale, obs, ranges, outs, n, M,
                                                          ppb, chunk);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
+}
+
+int launch_peers_wait(rl_method* m) {
+  peers_wait_kernel<<<1, 32, 0, m->stream>>>(m->peer_cfg);
   count_launch();
   RL_CHECK_LAUNCH();
   return RL_OK;

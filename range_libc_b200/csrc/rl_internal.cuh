@@ -89,6 +89,17 @@ struct PeerOut {
   double* ptr[RL_MAX_PEERS];
   int n;             // 0: write only the local `weights` array
   long long offset;  // first particle of this rank inside the gathered array
+  // Signalled mode (sig != 0): no separate barrier.  Every launch is one "epoch" e = *epoch + 1.  The
+  // kernel first waits until every rank has finished epoch e-1 (flags written by the peers into OUR
+  // flag array), stores its weights into buffer e & 1 of every rank (ptr = buffer 0, ptr1 = buffer 1),
+  // and the last CTA to finish publishes flags[r][rank] = e on every rank r.  Double buffering makes
+  // the start-of-kernel wait sufficient for reuse safety.
+  int sig;
+  int rank;
+  double* ptr1[RL_MAX_PEERS];
+  long long* flags[RL_MAX_PEERS];  // flags[r] = rank r's flag array (n entries), peer mapped
+  long long* epoch;                // local: epochs completed by this rank
+  unsigned* counter;               // local: CTAs finished in the current launch
 };
 
 }  // namespace rl
@@ -131,6 +142,12 @@ struct rl_method {
   // sensor model
   double* d_table = nullptr;
   int K = 0;
+  // multi-GPU signalled all-gather state (rl_method_peers_init)
+  rl::PeerOut peer_cfg{};
+  bool peers_ready = false;
+  long long* d_epoch = nullptr;
+  unsigned* d_counter = nullptr;
+  long long host_epoch = 0;
   // staging for host-pointer calls
   void* d_stage = nullptr;
   size_t d_stage_bytes = 0;
@@ -163,4 +180,5 @@ int launch_cast(rl_method* m, int mode, const float* d_ins, const float* d_angle
                 double* d_weights, int n, int num_angles, const PeerOut* peers = nullptr);
 int launch_eval_sensor(rl_method* m, const float* d_obs, const float* d_ranges, double* d_outs, int m_rays, int n);
 int launch_sincosf(const float* d_x, float* d_s, float* d_c, int n, cudaStream_t st);
+int launch_peers_wait(rl_method* m);
 }  // namespace rl

@@ -91,3 +91,41 @@ class PeerStoreSensorUpdate:
                                                                      self.peer_ptrs, self.lo)
         self.handle.barrier()  # every rank's stores have landed before anyone reads weights_all
         return self.weights_all
+
+
+class SignalledSensorUpdate:
+    """Fused compute + all-gather + synchronisation in ONE kernel per rank and step
+    (rl_calc_range_repeat_angles_eval_sensor_model_signalled): weights are double buffered in symmetric
+    memory, completion is signalled through peer-written epoch flags, and the only extra launch is the
+    consumer-side wait (update(..., wait=True)) before the gathered weights are read.  GPU only."""
+
+    def __init__(self, n_total, method, angles, obs, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.dist = dist
+        self.group = group or dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n_total = n_total
+        self.lo, self.hi = particle_slice(n_total, self.rank, self.world)
+        self.method, self.angles, self.obs = method, angles, obs
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm_mem.empty(n_total, dtype=torch.float64, device=device)
+            self.bufs.append(t)
+            self.handles.append(symm_mem.rendezvous(t, self.group))
+        self.flags = symm_mem.empty(max(self.world, 2), dtype=torch.int64, device=device)
+        self.flags.zero_()
+        self.flag_handle = symm_mem.rendezvous(self.flags, self.group)
+        torch.cuda.synchronize()
+        self.flag_handle.barrier()  # every rank's flags are zero before anyone can signal
+        torch.cuda.synchronize()
+        method.peers_init([int(p) for p in self.handles[0].buffer_ptrs], [int(p) for p in self.handles[1].buffer_ptrs],
+                          [int(p) for p in self.flag_handle.buffer_ptrs], self.rank)
+
+    def update(self, local_particles, wait=True):
+        b = self.method.calc_range_repeat_angles_eval_sensor_model_signalled(local_particles, self.angles, self.obs, self.lo)
+        if wait:
+            self.method.peers_wait()
+        return self.bufs[b]

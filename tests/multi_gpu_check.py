@@ -54,8 +54,22 @@ def main():
         results["peer"] = np.array_equal(w2.cpu().numpy().view(np.uint64), ref.view(np.uint64))
     except Exception as ex:  # noqa: BLE001
         results["peer"] = "unavailable: %s" % str(ex).splitlines()[0]
+    try:
+        sig = parallel.SignalledSensorUpdate(n_total, rm, angles, obs, device=dev)
+        ok_all = True
+        for it in range(6):  # several epochs back to back: both buffers, flag reuse
+            shift = torch.tensor([0.25 * it, -0.5 * it, 0.01 * it], device=dev)
+            w3 = sig.update(mine + shift, wait=True)
+            torch.cuda.synchronize()
+            if it in (0, 5):
+                ref_it = ora.calc_range_repeat_angles_eval_sensor_model(
+                    (torch.from_numpy(particles).to(dev) + shift).cpu().numpy(), angles_h, obs_h)
+                ok_all &= bool(np.array_equal(w3.cpu().numpy().view(np.uint64), ref_it.view(np.uint64)))
+        results["signalled"] = ok_all
+    except Exception as ex:  # noqa: BLE001
+        results["signalled"] = "unavailable: %s" % str(ex).splitlines()[0]
     print("rank %d/%d: %s" % (rank, world, results), flush=True)
-    ok = results["nccl"] is True and results["peer"] in (True,) or isinstance(results["peer"], str)
+    ok = results["nccl"] is True and all(results[k] is True or isinstance(results[k], str) for k in ("peer", "signalled"))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
