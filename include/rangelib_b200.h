@@ -35,8 +35,8 @@ typedef struct rl_map rl_map;
 typedef struct rl_method rl_method;
 
 /* range method kinds (RangeLib.h: BresenhamsLine :691, RayMarching :922 / RayMarchingGPU :774,
- * CDDTCast :971; PCDDT = CDDTCast + prune() :1176) */
-enum { RL_BL = 0, RL_RM = 1, RL_CDDT = 2, RL_PCDDT = 3 };
+ * CDDTCast :971; PCDDT = CDDTCast + prune() :1176; GiantLUTCast :1772) */
+enum { RL_BL = 0, RL_RM = 1, RL_CDDT = 2, RL_PCDDT = 3, RL_GLT = 4 };
 
 enum {
   RL_OK = 0,
@@ -70,7 +70,8 @@ void rl_map_destroy(rl_map* map);
 
 /* ---- RangeMethod construction ------------------------------------------------------------ */
 /* replaces BresenhamsLine(OMap,mr) :694, RayMarching(OMap,mr) :925, RayMarchingGPU(OMap,mr) :777,
- * CDDTCast(OMap,mr,td) :974 (+ prune for RL_PCDDT).  The map (and its world parameters) is
+ * CDDTCast(OMap,mr,td) :974 (+ prune for RL_PCDDT), GiantLUTCast(OMap,mr,td) :1781 (the W*H*td uint16
+ * table is filled on the device by the RM kernel).  The map (and its world parameters) is
  * copied, like the reference's by-value OMap.  All acceleration structures (distance
  * transform, CDDT tables) are BUILT ON THE DEVICE and stay resident there.
  * device < 0 selects the current CUDA device. */
@@ -162,6 +163,8 @@ int rl_debug_set_coop_threshold(rl_method* m, int lanes);
 /* tuning knob (RM): large batches use persistent warps with lane re-queuing (default 1) or the
  * one-ray-per-thread kernel (0).  Results are identical. */
 int rl_debug_set_persistent(rl_method* m, int on);
+/* GiantLUTCast::giant_lut (RangeLib.h:1903) as out[(x*H + y)*td + i], W*H*td uint16; HOST buffer */
+int rl_debug_glt_dump(rl_method* m, uint16_t* out);
 /* device trig used by BL/RM (restated glibc sinf/cosf); HOST buffers; for tests */
 int rl_debug_sincosf(const float* x, float* s, float* c, int n);
 

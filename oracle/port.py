@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-BL, RM, CDDT, PCDDT = 0, 1, 2, 3
+BL, RM, CDDT, PCDDT, GLT = 0, 1, 2, 3, 4
 
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)
@@ -56,6 +56,8 @@ def _load():
     L.orc_calc_range.restype = C.c_float
     L.orc_calc_range.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
     L.orc_rm_step_counts.argtypes = [C.c_void_p, _f32p, _i32p, C.c_int]
+    L.orc_glt.restype = C.POINTER(C.c_uint16)
+    L.orc_glt.argtypes = [C.c_void_p]
     L.orc_dt.restype = _f32p
     L.orc_dt.argtypes = [C.c_void_p]
     for name, rt in [("orc_cddt_nbins", C.c_int64), ("orc_cddt_nvalues", C.c_int64), ("orc_cddt_widths", _i32p),
@@ -181,6 +183,10 @@ class Oracle:
     def dt(self):
         ptr = self.L.orc_dt(self.h)
         return np.ctypeslib.as_array(ptr, shape=(self.width, self.height)).copy()
+
+    def glt_table(self):
+        ptr = self.L.orc_glt(self.h)
+        return np.ctypeslib.as_array(ptr, shape=(self.width, self.height, self.td)).copy()
 
     def cddt_table(self):
         nb = self.L.orc_cddt_nbins(self.h)

@@ -222,7 +222,10 @@ typedef struct {
   /* sensor model */
   int K;
   double* table;
-  int kind; /* 0 BL 1 RM 2 CDDT */
+  int kind; /* 0 BL 1 RM 2 CDDT 4 GLT */
+  /* GiantLUTCast */
+  uint16_t* glt; /* [(x*H + y)*td + i] */
+  float max_div_limits, limits_div_max;
 } orc_ctx;
 
 static inline int occ_at(const orc_ctx* c, int x, int y) { /* OMap::isOccupied RangeLib.h:204-210 */
@@ -590,10 +593,49 @@ static float cddt_calc_range(const orc_ctx* c, float x, float y, float heading) 
   return -1.0f; /* the reference's assert(0) fall-through (:1514) */
 }
 
+/* ------------------------------------------------------------------------------------------
+ * GiantLUTCast, RangeLib.h:1772-1904 (_GIANT_LUT_SHORT_DATATYPE 1, _USE_CACHED_CONSTANTS 1,
+ * _USE_ALTERNATE_MOD 1, _USE_FAST_ROUND 0): a uint16 range for every (x, y, theta bin), seeded by
+ * RayMarching from the pixel CORNER (x, y) (:1801)
+ * ------------------------------------------------------------------------------------------ */
+static void glt_build(orc_ctx* c) {
+  unsigned td = c->td;
+  float step = cddt_M_2PI_div_td(td);                       /* :1784, same expression as CDDT's */
+  c->max_div_limits = c->max_range / (float)65535;          /* :1785 */
+  c->limits_div_max = (float)65535 / c->max_range;          /* :1786 */
+  c->glt = (uint16_t*)malloc((size_t)c->W * c->H * td * sizeof(uint16_t));
+  size_t k = 0;
+  for (int x = 0; x < c->W; ++x)
+    for (int y = 0; y < c->H; ++y)
+      for (unsigned i = 0; i < td; ++i) {
+        float angle = (float)(int)i * step;                  /* :1797 */
+        float r = rm_calc_range(c, (float)x, (float)y, angle);
+        r = (r < c->max_range) ? r : c->max_range;           /* std::min(max_range, r) :1804 */
+        c->glt[k++] = (uint16_t)(int)(r * c->limits_div_max); /* :1806 */
+      }
+}
+
+static int glt_discretize_theta(unsigned td, float theta) { /* :1833-1867 */
+  if ((double)theta < 0.0) {
+    while ((double)theta < 0.0) theta = (float)((double)theta + ORC_M_2PI);
+  } else if ((double)theta > ORC_M_2PI) {
+    while ((double)theta > ORC_M_2PI) theta = (float)((double)theta - ORC_M_2PI);
+  }
+  int rounded = (int)roundf(theta * cddt_td_div_M_2PI(td));
+  return rounded % (int)td;
+}
+
+static float glt_calc_range(const orc_ctx* c, float x, float y, float heading) { /* :1869-1880 */
+  if (x < 0 || x >= (float)(unsigned)c->W || y < 0 || y >= (float)(unsigned)c->H) return c->max_range;
+  int i = glt_discretize_theta(c->td, heading);
+  return (float)(int)c->glt[((size_t)(int)x * c->H + (int)y) * c->td + i] * c->max_div_limits;
+}
+
 static float calc_range_any(const orc_ctx* c, float x, float y, float th) {
   switch (c->kind) {
     case 0: return bl_calc_range(c, x, y, th);
     case 1: return rm_calc_range(c, x, y, th);
+    case 4: return glt_calc_range(c, x, y, th);
     default: return cddt_calc_range(c, x, y, th);
   }
 }
@@ -613,9 +655,10 @@ orc_ctx* orc_create(int kind, const uint8_t* occ, int W, int H, float max_range,
   c->world_scale = 1.0f;
   c->world_cos_angle = 1.0f;
   c->td = td;
-  if (c->kind == 1) {
+  if (c->kind == 1 || c->kind == 4) {
     c->dt = (float*)malloc((size_t)W * H * sizeof(float));
     orc_edt(c->occ, W, H, c->dt);
+    if (c->kind == 4) glt_build(c);
   } else if (c->kind == 2) {
     cddt_build(c);
     if (kind == 3) cddt_prune(c, max_range);
@@ -632,6 +675,7 @@ void orc_destroy(orc_ctx* c) {
   free(c->offsets);
   free(c->values);
   free(c->table);
+  free(c->glt);
   free(c);
 }
 
@@ -652,6 +696,7 @@ int64_t orc_prune_unassigned(const orc_ctx* c) { return c->prune_unassigned; }
 float orc_calc_range(const orc_ctx* c, float x, float y, float th) { return calc_range_any(c, x, y, th); }
 
 const float* orc_dt(const orc_ctx* c) { return c->dt; }
+const uint16_t* orc_glt(const orc_ctx* c) { return c->glt; }
 int64_t orc_cddt_nbins(const orc_ctx* c) { return c->slice0 ? c->slice0[c->td] : 0; }
 int64_t orc_cddt_nvalues(const orc_ctx* c) { return c->offsets ? c->offsets[c->slice0[c->td]] : 0; }
 const int* orc_cddt_widths(const orc_ctx* c) { return c->widths; }

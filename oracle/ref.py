@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-BL, RM, CDDT, PCDDT = 0, 1, 2, 3
+BL, RM, CDDT, PCDDT, GLT = 0, 1, 2, 3, 4
 
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)
@@ -61,6 +61,7 @@ def _load(flavor):
     L.ref_cddt_dims.restype = C.c_int64
     L.ref_cddt_dims.argtypes = [C.c_void_p, _i64p, _i32p, _f32p]
     L.ref_cddt_dump.argtypes = [C.c_void_p, _i64p, _f32p]
+    L.ref_glt_dump.argtypes = [C.c_void_p, C.POINTER(C.c_uint16), C.c_int]
     _libs[flavor] = L
     return L
 
@@ -178,6 +179,12 @@ class RefMethod:
         values = np.zeros(max(nv.value, 1), np.float32)
         self.L.ref_cddt_dump(self.h, _p(offsets, _i64p), _p(values, _f32p))
         return widths, trans, offsets, values[: nv.value]
+
+    def glt_table(self, theta_disc):
+        out = np.zeros((self.map.width, self.map.height, theta_disc), np.uint16)
+        if self.L.ref_glt_dump(self.h, out.ctypes.data_as(C.POINTER(C.c_uint16)), theta_disc) != 0:
+            raise ValueError("not a GLT method")
+        return out
 
     def __del__(self):
         if getattr(self, "h", None):

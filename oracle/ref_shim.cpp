@@ -28,12 +28,19 @@ struct RMOpen : public ranges::RayMarching {
   float dt_at(int x, int y) { return distImage.get(x, y); }
 };
 
+// GiantLUTCast::giant_lut is protected (RangeLib.h:1895-1903); expose it read-only.
+struct GLTOpen : public ranges::GiantLUTCast {
+  GLTOpen(ranges::OMap m, float mr, int td) : ranges::GiantLUTCast(m, mr, td) {}
+  uint16_t at(int x, int y, int i) { return giant_lut[x][y][i]; }
+};
+
 struct RefMethod {
-  int kind;  // 0 BL, 1 RM, 2 CDDT (prune() turns it into PCDDT)
+  int kind;  // 0 BL, 1 RM, 2 CDDT (prune() turns it into PCDDT), 4 GLT
   ranges::RangeMethod* base = nullptr;
   ranges::BresenhamsLine* bl = nullptr;
   RMOpen* rm = nullptr;
   ranges::CDDTCast* cddt = nullptr;
+  GLTOpen* glt = nullptr;
 };
 
 template <class F>
@@ -129,11 +136,26 @@ void* ref_method_create(int kind, void* mp, float max_range, unsigned td) {
     r->cddt = new ranges::CDDTCast(*m, max_range, td);
     if (kind == 3) r->cddt->prune(max_range);
     r->base = r->cddt;
+  } else if (kind == 4) {
+    r->glt = new GLTOpen(*m, max_range, (int)td);
+    r->base = r->glt;
   } else {
     delete r;
     return nullptr;
   }
   return r;
+}
+
+// GiantLUTCast table dump: out[(x*H + y)*td + i]
+int ref_glt_dump(void* rp, uint16_t* out, int td) {
+  RefMethod* r = (RefMethod*)rp;
+  if (!r->glt) return -1;
+  ranges::OMap* m = r->glt->getMap();
+  size_t k = 0;
+  for (unsigned x = 0; x < m->width; ++x)
+    for (unsigned y = 0; y < m->height; ++y)
+      for (int i = 0; i < td; ++i) out[k++] = r->glt->at(x, y, i);
+  return 0;
 }
 
 void ref_method_destroy(void* rp) {

@@ -49,6 +49,7 @@ class PyOMap:
 
     def __init__(self, arg1, arg2=None):
         self._h = C.c_void_p()
+        self._L = lib()  # kept so that __del__ works during interpreter shutdown
         world = None
         if isinstance(arg1, (int, np.integer)) and isinstance(arg2, (int, np.integer)):
             occ = np.zeros((int(arg1), int(arg2)), np.uint8)
@@ -102,9 +103,9 @@ class PyOMap:
         check(lib().rl_map_update(self._h, C.c_void_p(p.ctypes.data), int(x0), int(y0), p.shape[0], p.shape[1]))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().rl_map_destroy(self._h)
-            self._h = C.c_void_p()
+        if getattr(self, "_h", None) and self._h.value and getattr(self, "_L", None) is not None:
+            self._L.rl_map_destroy(self._h)
+            self._h.value = None
 
 
 class _RangeMethod:
@@ -112,6 +113,7 @@ class _RangeMethod:
 
     def __init__(self, Map, max_range, theta_disc=0, device=-1):
         self._h = C.c_void_p()
+        self._L = lib()
         self.max_range = float(max_range)
         self._map = Map
         check(lib().rl_method_create(self._kind, Map._h, float(max_range), int(theta_disc), int(device),
@@ -240,9 +242,9 @@ class _RangeMethod:
         check(lib().rl_debug_set_coop_threshold(self._h, int(lanes)))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().rl_method_destroy(self._h)
-            self._h = C.c_void_p()
+        if getattr(self, "_h", None) and self._h.value and getattr(self, "_L", None) is not None:
+            self._L.rl_method_destroy(self._h)
+            self._h.value = None
 
 
 class PyBresenhamsLine(_RangeMethod):
@@ -289,6 +291,21 @@ class PyCDDTCast(_RangeMethod):
         values = np.zeros(max(nv.value, 1), np.float32)
         check(lib().rl_debug_cddt_dump(self._h, C.c_void_p(offsets.ctypes.data), C.c_void_p(values.ctypes.data)))
         return widths, trans, offsets, values[: nv.value]
+
+
+class PyGiantLUTCast(_RangeMethod):
+    """GiantLUTCast (RangeLib.h:1772-1904): uint16 range for every (x, y, theta bin); the W*H*td table is
+    filled on the device by the RM kernel and a query is one gather."""
+    _kind = cabi.RL_GLT
+
+    def __init__(self, Map, max_range, theta_disc, device=-1):
+        self.theta_disc = int(theta_disc)
+        super().__init__(Map, max_range, theta_disc, device)
+
+    def table(self):
+        out = np.empty((self._map.width(), self._map.height(), self.theta_disc), np.uint16)
+        check(lib().rl_debug_glt_dump(self._h, C.c_void_p(out.ctypes.data)))
+        return out
 
 
 def device_sincosf(x):

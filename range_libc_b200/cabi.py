@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librangelib_b200.so")
 
-RL_BL, RL_RM, RL_CDDT, RL_PCDDT = 0, 1, 2, 3
+RL_BL, RL_RM, RL_CDDT, RL_PCDDT, RL_GLT = 0, 1, 2, 3, 4
 RL_OK, RL_E_INVALID, RL_E_CUDA, RL_E_NO_DEVICE, RL_E_STATE, RL_E_MIXED = 0, -1, -2, -3, -4, -5
 
 _vp = C.c_void_p
@@ -48,6 +48,7 @@ SIGNATURES = {
     "rl_debug_get_dt": (_i, [_vp, _vp]),
     "rl_debug_cddt_dims": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, _vp]),
     "rl_debug_cddt_dump": (_i, [_vp, _vp, _vp]),
+    "rl_debug_glt_dump": (_i, [_vp, _vp]),
     "rl_debug_sincosf": (_i, [_vp, _vp, _vp, _i]),
     "rl_debug_set_coop_threshold": (_i, [_vp, _i]),
     "rl_debug_set_persistent": (_i, [_vp, _i]),

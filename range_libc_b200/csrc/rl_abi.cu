@@ -238,6 +238,7 @@ static void free_method(rl_method* m) {
   cudaFree(m->d_bits_y);
   cudaFree(m->d_bits_x);
   cudaFree(m->d_dt);
+  cudaFree(m->d_glt);
   cudaFree(m->d_table);
   cudaFree(m->d_stage);
   cudaFree(m->d_epoch);
@@ -313,7 +314,7 @@ int rl_map_update(rl_map* map, const uint8_t* patch, int x0, int y0, int w, int 
 void rl_map_destroy(rl_map* map) { delete map; }
 
 int rl_method_create(int kind, const rl_map* map, float max_range, unsigned td, int device, rl_method** out) {
-  if (!map || !out || kind < RL_BL || kind > RL_PCDDT) {
+  if (!map || !out || kind < RL_BL || kind > RL_GLT) {
     set_error("rl_method_create: bad arguments");
     return RL_E_INVALID;
   }
@@ -356,7 +357,12 @@ int rl_method_create(int kind, const rl_map* map, float max_range, unsigned td, 
   if (e != cudaSuccess) rc = cuda_fail(e, "stream create", __FILE__, __LINE__);
   m->stream = m->own_stream;
   if (!rc) rc = upload_occupancy(m, map);
-  if (!rc && kind == RL_RM) rc = build_distance_transform(m);
+  if (!rc && kind == RL_GLT && td == 0) {
+    set_error("GiantLUTCast: theta_discretization must be > 0");
+    rc = RL_E_INVALID;
+  }
+  if (!rc && (kind == RL_RM || kind == RL_GLT)) rc = build_distance_transform(m);
+  if (!rc && kind == RL_GLT) rc = glt_build(m);
   if (!rc && (kind == RL_CDDT || kind == RL_PCDDT)) rc = cddt_build(m);
   if (!rc && kind == RL_PCDDT) rc = cddt_prune(m, max_range);
   if (!rc) {
@@ -418,7 +424,8 @@ int rl_method_update_map(rl_method* m, const uint8_t* patch, int x0, int y0, int
   }
   rc = apply_patch(m, d_patch, x0, y0, w, h);
   if (rc) return rc;
-  if (m->kind == RL_RM) rc = build_distance_transform(m);
+  if (m->kind == RL_RM || m->kind == RL_GLT) rc = build_distance_transform(m);
+  if (!rc && m->kind == RL_GLT) rc = glt_build(m);
   if (m->kind == RL_CDDT || m->kind == RL_PCDDT) {
     const bool was_pruned = m->pruned;
     rc = cddt_build(m);
@@ -442,8 +449,9 @@ int rl_debug_set_persistent(rl_method* m, int on) {
 int64_t rl_method_memory(const rl_method* m) {
   if (!m) return RL_E_INVALID;
   int64_t bytes = (int64_t)m->W * m->H + (int64_t)m->W * m->wpy * 4 + (int64_t)m->H * m->wpx * 4;
-  if (m->kind == RL_RM) bytes += (int64_t)m->dt_elems() * 4;
-  if (m->kind >= RL_CDDT) bytes += m->nvalues * 4 + (m->nbins + 1) * 8 + (int64_t)m->td * 16;
+  if (m->kind == RL_RM || m->kind == RL_GLT) bytes += (int64_t)m->dt_elems() * 4;
+  if (m->kind == RL_GLT) bytes += (int64_t)m->W * m->H * m->td * 2;
+  if (m->kind == RL_CDDT || m->kind == RL_PCDDT) bytes += m->nvalues * 4 + (m->nbins + 1) * 8 + (int64_t)m->td * 16;
   return bytes;
 }
 
@@ -634,7 +642,7 @@ int rl_debug_get_dt(rl_method* m, float* out) {
 int rl_debug_cddt_dims(rl_method* m, int64_t* n_bins, int64_t* n_values, int* widths, float* translations) {
   int rc = bind(m);
   if (rc) return rc;
-  if (m->kind < RL_CDDT) {
+  if (m->kind != RL_CDDT && m->kind != RL_PCDDT) {
     set_error("not a CDDT method");
     return RL_E_STATE;
   }
@@ -648,13 +656,25 @@ int rl_debug_cddt_dims(rl_method* m, int64_t* n_bins, int64_t* n_values, int* wi
 int rl_debug_cddt_dump(rl_method* m, int64_t* offsets, float* values) {
   int rc = bind(m);
   if (rc) return rc;
-  if (m->kind < RL_CDDT || !offsets || !values) {
+  if ((m->kind != RL_CDDT && m->kind != RL_PCDDT) || !offsets || !values) {
     set_error("not a CDDT method");
     return RL_E_STATE;
   }
   RL_CUDA(cudaMemcpyAsync(offsets, m->d_offsets, sizeof(int64_t) * ((size_t)m->nbins + 1), cudaMemcpyDeviceToHost, m->stream));
   if (m->nvalues)
     RL_CUDA(cudaMemcpyAsync(values, m->d_values, sizeof(float) * (size_t)m->nvalues, cudaMemcpyDeviceToHost, m->stream));
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  return RL_OK;
+}
+
+int rl_debug_glt_dump(rl_method* m, uint16_t* out) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (m->kind != RL_GLT || !m->d_glt || !out) {
+    set_error("rl_debug_glt_dump: not a GiantLUT method");
+    return RL_E_STATE;
+  }
+  RL_CUDA(cudaMemcpyAsync(out, m->d_glt, sizeof(uint16_t) * (size_t)m->W * m->H * m->td, cudaMemcpyDeviceToHost, m->stream));
   RL_CUDA(cudaStreamSynchronize(m->stream));
   return RL_OK;
 }

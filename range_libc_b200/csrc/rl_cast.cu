@@ -373,11 +373,35 @@ __device__ __forceinline__ float cddt_cast(const MapView& mv, const CddtView& cv
   return -1.0f;  // the reference's assert(0) fall-through (:1514)
 }
 
+// GiantLUTCast::calc_range RangeLib.h:1869-1880 with discretize_theta :1833-1867 (no flip, unlike CDDT)
+__device__ __forceinline__ float glt_cast(const MapView& mv, float max_range, float x, float y, float theta) {
+  if (!finite3(x, y, theta)) return max_range;
+  if (x < 0.0f || x >= (float)(unsigned)mv.W || y < 0.0f || y >= (float)(unsigned)mv.H) return max_range;
+  if ((double)theta < 0.0) {
+    int it = 0;
+    while ((double)theta < 0.0) {
+      theta = __double2float_rn((double)theta + RL_M_2PI);
+      if (++it > 1000) { theta = __double2float_rn(fmod((double)theta, RL_M_2PI) + RL_M_2PI); }
+    }
+  } else if ((double)theta > RL_M_2PI) {
+    int it = 0;
+    while ((double)theta > RL_M_2PI) {
+      theta = __double2float_rn((double)theta - RL_M_2PI);
+      if (++it > 1000) { theta = __double2float_rn(fmod((double)theta, RL_M_2PI)); }
+    }
+  }
+  const int rounded = (int)roundf(fmul(theta, mv.glt_td_div_2pi));
+  const int i = rounded % (int)mv.glt_td;
+  const size_t cell = (size_t)__float2int_rz(x) * (unsigned)mv.H + __float2int_rz(y);
+  return fmul((float)(int)__ldg(mv.glt + cell * mv.glt_td + i), mv.glt_max_div_limits);
+}
+
 template <int KIND>
 __device__ __forceinline__ float cast_one(const MapView& mv, const CddtView& cv, float max_range, float x, float y,
                                           float th) {
   if (KIND == RL_BL) return bl_cast(mv, max_range, x, y, th);
   if (KIND == RL_RM) return rm_cast(mv, max_range, x, y, th);
+  if (KIND == RL_GLT) return glt_cast(mv, max_range, x, y, th);
   return cddt_cast(mv, cv, max_range, x, y, th);
 }
 
@@ -411,7 +435,15 @@ template <int MODE>
 __device__ __forceinline__ void load_pose(const WorldXform& xf, const float* __restrict__ ins,
                                           const float* __restrict__ angles, long long r, int M, float* gx, float* gy,
                                           float* gth) {
-  if (MODE == MODE_GRID) {
+  if (MODE == MODE_GLT_BUILD) {
+    // table entry r = (x*H + y)*td + i: RM seeded from the pixel corner (x, y) at angle i * 2pi/td
+    // (RangeLib.h:1791-1801); M = td, xf.rot carries (float)(M_2PI / (float)td), xf.oy carries H
+    const long long cell = r / M;
+    const int Hh = (int)xf.oy;
+    *gx = (float)(int)(cell / Hh);
+    *gy = (float)(int)(cell % Hh);
+    *gth = fmul((float)(int)(r - cell * M), xf.rot);
+  } else if (MODE == MODE_GRID) {
     *gx = __ldg(ins + 3 * r);
     *gy = __ldg(ins + 3 * r + 1);
     *gth = __ldg(ins + 3 * r + 2);
@@ -623,7 +655,6 @@ rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
 
   // all ray bookkeeping is relative to `begin` (chunk <= 2^20) to keep the state in 32-bit registers
   const int count = (int)(end - begin);
-  outs += begin;
   int next_setup = 0;  // first ray of the chunk that has not been set up yet
   int batch_base = 0;  // ray of q[0]
   int batch_n = 0, batch_pos = 0;
@@ -682,7 +713,13 @@ rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
         done = rm_step(mv, max_range, x0, y0, dx, dy, t, result);
       } while (!done && --burst);
       if (done) {
-        outs[id] = (MODE == MODE_GRID) ? result : fmul(result, out_scale);
+        if (MODE == MODE_GLT_BUILD) {
+          // r = min(max_range, r); uint16 val = r * limits_div_max (RangeLib.h:1804-1806); xf.scale carries the factor
+          const float rr = (result < max_range) ? result : max_range;
+          ((uint16_t*)outs)[begin + id] = (uint16_t)__float2int_rz(fmul(rr, xf.scale));
+        } else {
+          outs[begin + id] = (MODE == MODE_GRID) ? result : fmul(result, out_scale);
+        }
         active = false;
       }
     }
@@ -763,6 +800,7 @@ int launch_cast(rl_method* m, int mode, const float* ins, const float* angles, c
   switch (m->kind) {
     case RL_BL: return launch_cast_kind<RL_BL>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
     case RL_RM: return launch_cast_kind<RL_RM>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
+    case RL_GLT: return launch_cast_kind<RL_GLT>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
     default: return launch_cast_kind<RL_CDDT>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
   }
 }
@@ -781,6 +819,32 @@ int launch_eval_sensor(rl_method* m, const float* obs, const float* ranges, doub
   const size_t smem = (size_t)ppb * chunk * sizeof(double);
   eval_sensor_kernel<<<grid, threads, smem, m->stream>>>(m->sensor_view(), m->xf.inv_scale, obs, ranges, outs, n, M,
                                                          ppb, chunk);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
+}
+
+// GiantLUTCast::GiantLUTCast (RangeLib.h:1781-1823): W*H*td RM casts, written as uint16
+int glt_build(rl_method* m) {
+  const long long total = (long long)m->W * m->H * m->td;
+  if (!m->d_glt) RL_CUDA(cudaMalloc(&m->d_glt, sizeof(uint16_t) * (size_t)(total > 0 ? total : 1)));
+  if (total == 0) return RL_OK;
+  MapView mv = m->map_view();
+  WorldXform xf{};
+  xf.rot = mv.glt_twopi_div_td;
+  xf.oy = (float)m->H;
+  xf.scale = mv.glt_limits_div_max;
+  if (!(m->max_range > 0.0f)) {  // every cast returns max_range without entering the loop
+    set_error("GiantLUTCast needs max_range > 0");
+    return RL_E_INVALID;
+  }
+  const long long resident_warps = (long long)sm_count() * 48;
+  long long per_warp = (total + resident_warps - 1) / resident_warps;
+  const int chunk = (int)min((long long)1 << 20, ((per_warp + 31) / 32) * 32);
+  const long long warps = (total + chunk - 1) / chunk;
+  const int grid = (int)((warps + 7) / 8);
+  rm_persist_kernel<MODE_GLT_BUILD><<<grid, 256, 0, m->stream>>>(mv, xf, m->max_range, nullptr, nullptr, (float*)m->d_glt,
+                                                               total, (int)m->td, chunk);
   count_launch();
   RL_CHECK_LAUNCH();
   return RL_OK;

@@ -59,6 +59,11 @@ struct MapView {
   int wpx;
   const float* dt;         // float distance transform (RM), x-major, see dt_index
   int coop_threshold;      // RM: warps with at most this many live rays finish them cooperatively (0 = off)
+  // GiantLUTCast (RangeLib.h:1772-1904): uint16 range per (x, y, theta bin), glt[(x*H + y)*td + i]
+  const uint16_t* glt;
+  unsigned glt_td;
+  float glt_td_div_2pi, glt_twopi_div_td;  // :1783-1784
+  float glt_max_div_limits, glt_limits_div_max;  // :1785-1786
 };
 
 struct CddtView {
@@ -79,7 +84,7 @@ struct SensorView {
   int K;
 };
 
-enum Mode { MODE_GRID = 0, MODE_WORLD = 1, MODE_ANGLES = 2, MODE_FUSED = 3 };
+enum Mode { MODE_GRID = 0, MODE_WORLD = 1, MODE_ANGLES = 2, MODE_FUSED = 3, MODE_GLT_BUILD = 4 };
 
 // Multi-GPU epilogue of the fused kernel: instead of one local array, the per-particle weights are
 // stored straight into the weight buffer of every peer GPU (peer-mapped device pointers over
@@ -128,6 +133,8 @@ struct rl_method {
   int wpx = 0;
   // RM
   float* d_dt = nullptr;
+  // GiantLUT
+  uint16_t* d_glt = nullptr;
   // CDDT
   int* d_widths = nullptr;
   float *d_trans = nullptr, *d_cosv = nullptr, *d_sinv = nullptr;
@@ -158,7 +165,16 @@ struct rl_method {
   size_t dt_elems() const { return (size_t)W * H; }
   int coop_threshold = 3;
   int persist = 1;  // RM large batches: 0 one ray per thread, 1 persistent warps with lane re-queuing
-  rl::MapView map_view() const { return rl::MapView{W, H, d_occ, d_bits_y, wpy, d_bits_x, wpx, d_dt, coop_threshold}; }
+  rl::MapView map_view() const {
+    rl::MapView v{W, H, d_occ, d_bits_y, wpy, d_bits_x, wpx, d_dt, coop_threshold, d_glt, td, 0.f, 0.f, 0.f, 0.f};
+    if (kind == RL_GLT && td) {
+      v.glt_td_div_2pi = (float)((double)td / RL_M_2PI);
+      v.glt_twopi_div_td = (float)(RL_M_2PI / (double)((float)td));
+      v.glt_max_div_limits = max_range / (float)65535;
+      v.glt_limits_div_max = (float)65535 / max_range;
+    }
+    return v;
+  }
   rl::CddtView cddt_view() const {
     return rl::CddtView{td, d_widths, d_trans, d_cosv, d_sinv, d_slice0, d_offsets, d_values, td_div_2pi, twopi_div_td};
   }
@@ -181,4 +197,5 @@ int launch_cast(rl_method* m, int mode, const float* d_ins, const float* d_angle
 int launch_eval_sensor(rl_method* m, const float* d_obs, const float* d_ranges, double* d_outs, int m_rays, int n);
 int launch_sincosf(const float* d_x, float* d_s, float* d_c, int n, cudaStream_t st);
 int launch_peers_wait(rl_method* m);
+int glt_build(rl_method* m);
 }  // namespace rl

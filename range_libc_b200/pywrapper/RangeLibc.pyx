@@ -7,6 +7,7 @@ Same classes and methods a particle filter written against the reference uses:
     PyOMap(bool_array | (w, h) | OccupancyGrid | png_path[, threshold])
     PyBresenhamsLine / PyRayMarching / PyRayMarchingGPU (omap, max_range)
     PyCDDTCast(omap, max_range, theta_disc)  (+ .prune())
+    PyGiantLUTCast(omap, max_range, theta_disc)
       .calc_range(x, y, heading)
       .calc_range_many(ins[N,3], outs[N])
       .calc_range_repeat_angles(ins[N,3], angles[M], outs[N*M])
@@ -32,6 +33,7 @@ cdef extern from "rangelib_b200.h":
         RL_RM
         RL_CDDT
         RL_PCDDT
+        RL_GLT
     const char* rl_last_error()
     uint64_t rl_stat_kernel_launches()
     int rl_map_create(const uint8_t* occ, int w, int h, rl_map** out)
@@ -232,7 +234,6 @@ cdef class PyCDDTCast(_Method):
         _ck(rl_method_prune(self.ptr, self.max_range if max_range < 0.0 else max_range))
 
 
-class PyGiantLUTCast:
-    def __init__(self, *a, **k):
-        raise NotImplementedError("GiantLUTCast is outside this backend's scope (SURVEY.md section 8f); "
-                                  "use PyCDDTCast or PyRayMarchingGPU")
+cdef class PyGiantLUTCast(_Method):
+    def __cinit__(self, PyOMap Map, float max_range, unsigned int theta_disc):
+        self._create(RL_GLT, Map, max_range, theta_disc)

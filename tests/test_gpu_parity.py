@@ -342,3 +342,29 @@ def test_bl_large_batches_and_reference_nontermination():
     qw = wl.grid_to_world(q, world[0], world[2], world[3])
     meth.calc_range_many(qw, out)
     assert_bit_equal(out, o.numpy_calc_range(qw), "world")
+
+
+def test_giant_lut_cast_gpu():
+    """GiantLUTCast: device-built W*H*td uint16 table and gather queries, bit-equal to the oracle; fused weights too."""
+    occ = wl.load_map("basement_hallways_10cm")
+    W, H = occ.shape
+    td = 36
+    m = rl.PyOMap(np.ascontiguousarray(occ.T.astype(bool)))
+    glt = rl.PyGiantLUTCast(m, MR, td)
+    o = port.Oracle(port.GLT, occ, MR, td)
+    assert np.array_equal(glt.table(), o.glt_table())
+    q = wl.random_queries(W, H, 100000, seed=3)
+    q[:10, 0] = [-1, 0, 599.9, 600, 601, 5, 5, 5, 5, 5]
+    q[:10, 2] = [0, 1, 2, 3, 4, -7, 7, 6.2831855, 6.28, 100]
+    out = np.empty(len(q), np.float32)
+    glt.calc_range_many_grid(q, out)
+    assert_bit_equal(out, o.calc_range_many(q), "glt grid")
+    parts = wl.pf_particles_uniform(occ, 300, seed=4)
+    angles = wl.lidar_angles(45)
+    obs = np.linspace(3, 480, 45).astype(np.float32)
+    glt.set_sensor_model(wl.sensor_table(501))
+    o.set_sensor_model(wl.sensor_table(501))
+    w = np.empty(len(parts), np.float64)
+    glt.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs, w)
+    assert_bit_equal(w, o.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs), "glt fused")
+    assert glt.memory() >= W * H * td * 2

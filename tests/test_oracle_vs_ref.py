@@ -54,3 +54,16 @@ def test_multithreaded_slicing_is_identical():
     rmap = ref.RefMap(occ=occ)
     c = ref.RefMethod(1, rmap, 500.0, threads=4).numpy_calc_range(q)
     assert_bit_equal(a, c)
+
+
+def test_giant_lut_cast():
+    """GiantLUTCast (RangeLib.h:1772-1904): table and queries, incl. out-of-map and wrapped headings."""
+    occ = wl.load_map("basement_hallways_10cm")[200:360, 250:400].copy()
+    q = wl.random_queries(occ.shape[0], occ.shape[1], 20000, seed=3)
+    q[:10, 0] = [-1, 0, 159.9, 160, 161, 5, 5, 5, 5, 5]
+    q[:10, 2] = [0, 1, 2, 3, 4, -7, 7, 6.2831855, 6.28, 100]
+    for td in (16, 108):
+        r = ref.RefMethod(ref.GLT, ref.RefMap(occ=occ), 300.0, td)
+        o = port.Oracle(port.GLT, occ, 300.0, td)
+        assert np.array_equal(r.glt_table(td), o.glt_table())
+        assert_bit_equal(o.calc_range_many(q), r.calc_range_many(q), "glt td %d" % td)
