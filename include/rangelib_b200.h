@@ -157,9 +157,9 @@ int rl_debug_get_dt(rl_method* m, float* out);
 int rl_debug_cddt_dims(rl_method* m, int64_t* n_bins, int64_t* n_values, int* widths, float* translations);
 /* offsets: n_bins+1 int64, values: n_values floats; HOST buffers */
 int rl_debug_cddt_dump(rl_method* m, int64_t* offsets, float* values);
-/* tuning knob (RM): a warp left with at most `lanes` unfinished rays finishes them one at a time with
- * all 32 lanes cooperating (default 3; 0 = off).  Results are identical. */
-int rl_debug_set_coop_threshold(rl_method* m, int lanes);
+/* tuning knob (RM, small launches): once a CTA (256 rays) has at most `rays` unfinished rays left they are
+ * finished one per warp with all 32 lanes cooperating (default 16; 0 = never hand off).  Results are identical. */
+int rl_debug_set_coop_threshold(rl_method* m, int rays);
 /* tuning knob (RM): large batches use persistent warps with lane re-queuing (default 1) or the
  * one-ray-per-thread kernel (0).  Results are identical. */
 int rl_debug_set_persistent(rl_method* m, int on);

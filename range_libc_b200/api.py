@@ -237,9 +237,9 @@ class _RangeMethod:
         """Tuning knob (RM): persistent-warp kernel with lane re-queuing for large batches."""
         check(lib().rl_debug_set_persistent(self._h, int(on)))
 
-    def set_coop_threshold(self, lanes):
-        """Tuning knob (RM): warps with <= lanes unfinished rays finish them cooperatively (0 = off)."""
-        check(lib().rl_debug_set_coop_threshold(self._h, int(lanes)))
+    def set_coop_threshold(self, rays):
+        """Tuning knob (RM, small launches): a CTA with <= rays live rays finishes them cooperatively (0 = off)."""
+        check(lib().rl_debug_set_coop_threshold(self._h, int(rays)))
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value and getattr(self, "_L", None) is not None:

@@ -436,7 +436,7 @@ int rl_method_update_map(rl_method* m, const uint8_t* patch, int x0, int y0, int
 
 int rl_debug_set_coop_threshold(rl_method* m, int lanes) {
   if (!m) return RL_E_INVALID;
-  m->coop_threshold = lanes < 0 ? 0 : (lanes > 32 ? 32 : lanes);
+  m->coop_threshold = lanes < 0 ? 0 : lanes;
   return RL_OK;
 }
 

@@ -117,40 +117,71 @@ __device__ __forceinline__ float rm_march_coop(const MapView& mv, float max_rang
   }
 }
 
-// Marches the rays held by the lanes of one warp to completion.  Must be called by all 32 lanes.
-// While many lanes hold a live ray every lane steps its own ray (rm_step) in short divergent
-// bursts; once at most mv.coop_threshold remain, they are finished one after the other by
-// rm_march_coop.
-#define RL_BURST 8
-__device__ __forceinline__ float rm_march_warp(const MapView& mv, float max_range, bool active, float x0, float y0,
-                                               float dx, float dy) {
+// Marches the rays held by the threads of one CTA (blockDim.x <= 256) to completion.  Must be called by
+// ALL threads of the CTA (it synchronises).
+//   phase 1  every thread steps its own ray (rm_step) in bursts of RL_BLOCK_BURST iterations; after each burst
+//            the CTA counts the rays still alive.  This finishes the bulk of the rays (mean ~6 steps) at one
+//            dependent L2 read per step and lane;
+//   phase 2  once at most mv.coop_threshold rays are left (default 16: two per warp) they are parked in shared
+//            memory and the warps of the CTA take them one at a time and finish each with all 32 lanes
+//            (rm_march_coop).  The long crawls along walls -- the rays that decide the duration of a small
+//            launch -- thus run concurrently on different warps, each at the cooperative rate, instead of
+//            holding a nearly empty warp each.
+// mv.coop_threshold == 0 (or a map / range too large for the 16-bit cell keys) keeps everything in phase 1.
+#define RL_BLOCK_BURST 8
+__device__ __forceinline__ float rm_march_block(const MapView& mv, float max_range, bool active, float x0, float y0,
+                                                float dx, float dy) {
+  __shared__ float4 s_ray[256];
+  __shared__ float s_t[256];
+  __shared__ float s_res[256];
+  __shared__ short s_slot[256];
+  __shared__ int s_n, s_next;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   float t = 0.0f, result = max_range;
-  const int coop = (mv.W < 32768 && mv.H < 32768 && max_range < 32768.0f) ? mv.coop_threshold : 0;
-  while (true) {
-    unsigned act = __ballot_sync(FULL, active);
-    if (!act) break;
-    if (__popc(act) <= coop) {
-      while (act) {
-        const int src = __ffs(act) - 1;
-        act &= act - 1;
-        const float r = rm_march_coop(mv, max_range, __shfl_sync(FULL, x0, src), __shfl_sync(FULL, y0, src),
-                                      __shfl_sync(FULL, dx, src), __shfl_sync(FULL, dy, src),
-                                      __shfl_sync(FULL, t, src));
-        if (lane == src) result = r;
+  const int handoff = (mv.W < 32768 && mv.H < 32768 && max_range < 32768.0f) ? min(mv.coop_threshold, 256) : 0;
+  if (handoff <= 0) {
+    if (active)
+      while (!rm_step(mv, max_range, x0, y0, dx, dy, t, result)) {
       }
-      break;
-    }
+    return result;
+  }
+  if (threadIdx.x == 0) {
+    s_n = 0;
+    s_next = 0;
+  }
+  while (true) {
     if (active) {
-      int n = RL_BURST;
+      int n = RL_BLOCK_BURST;
       bool done;
       do {
         done = rm_step(mv, max_range, x0, y0, dx, dy, t, result);
       } while (!done && --n);
       active = !done;
     }
+    const int alive = __syncthreads_count(active);
+    if (alive == 0) return result;
+    if (alive <= handoff) break;
   }
+  if (active) {
+    const int q = atomicAdd(&s_n, 1);
+    s_ray[q] = make_float4(x0, y0, dx, dy);
+    s_t[q] = t;
+    s_slot[q] = (short)threadIdx.x;
+  }
+  __syncthreads();
+  const int n_long = s_n;
+  while (true) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(&s_next, 1);
+    q = __shfl_sync(FULL, q, 0);
+    if (q >= n_long) break;
+    const float4 ray = s_ray[q];
+    const float r = rm_march_coop(mv, max_range, ray.x, ray.y, ray.z, ray.w, s_t[q]);
+    if (lane == 0) s_res[s_slot[q]] = r;
+  }
+  __syncthreads();
+  if (active) result = s_res[threadIdx.x];
   return result;
 }
 
@@ -458,16 +489,14 @@ __device__ __forceinline__ void load_pose(const WorldXform& xf, const float* __r
   }
 }
 
-// one ray per thread, grid-stride; the loop is warp-uniform so that RM can march at warp level
+// one ray per thread, grid-stride; the loop is CTA-uniform so that RM can march at CTA level (rm_march_block)
 template <int KIND, int MODE>
 __global__ void __launch_bounds__(256, KIND == RL_RM ? 7 : 4)
 cast_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float* __restrict__ ins,
             const float* __restrict__ angles, float* __restrict__ outs, long long total, int M) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long first = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);  // this warp's first ray
-  const int lane = threadIdx.x & 31;
-  for (long long base = first; base < total; base += stride) {
-    const long long r = base + lane;
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride) {  // CTA-uniform trip count
+    const long long r = base + threadIdx.x;
     const bool valid = r < total;
     float gx = 0.f, gy = 0.f, gth = 0.f;
     if (valid) load_pose<MODE>(xf, ins, angles, r, M, &gx, &gy, &gth);
@@ -475,7 +504,7 @@ cast_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float
     if (KIND == RL_RM) {
       float dx = 0.f, dy = 0.f;
       const bool ok = valid && rm_setup(max_range, gx, gy, gth, &dx, &dy);
-      range = rm_march_warp(mv, max_range, ok, gx, gy, dx, dy);
+      range = rm_march_block(mv, max_range, ok, gx, gy, dx, dy);
     } else {
       range = valid ? cast_one<KIND>(mv, cv, max_range, gx, gy, gth) : 0.0f;
     }
@@ -532,7 +561,7 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
         if (KIND == RL_RM) {
           float dx = 0.f, dy = 0.f;
           const bool ok = valid && rm_setup(max_range, gx, gy, gth, &dx, &dy);
-          d = rm_march_warp(mv, max_range, ok, gx, gy, dx, dy);
+          d = rm_march_block(mv, max_range, ok, gx, gy, dx, dy);
         } else {
           d = valid ? cast_one<KIND>(mv, cv, max_range, gx, gy, gth) : 0.0f;
         }

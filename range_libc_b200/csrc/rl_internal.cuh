@@ -58,7 +58,7 @@ struct MapView {
   const uint32_t* bits_x;  // the same grid packed along x: word (y, x>>5), bit x&31; row stride wpx words
   int wpx;
   const float* dt;         // float distance transform (RM), x-major, see dt_index
-  int coop_threshold;      // RM: warps with at most this many live rays finish them cooperatively (0 = off)
+  int coop_threshold;      // RM: a CTA with at most this many live rays finishes them cooperatively, one per warp (0 = off)
   // GiantLUTCast (RangeLib.h:1772-1904): uint16 range per (x, y, theta bin), glt[(x*H + y)*td + i]
   const uint16_t* glt;
   unsigned glt_td;
@@ -163,7 +163,7 @@ struct rl_method {
   size_t h_stage_bytes = 0;
 
   size_t dt_elems() const { return (size_t)W * H; }
-  int coop_threshold = 3;
+  int coop_threshold = 16;
   int persist = 1;  // RM large batches: 0 one ray per thread, 1 persistent warps with lane re-queuing
   rl::MapView map_view() const {
     rl::MapView v{W, H, d_occ, d_bits_y, wpy, d_bits_x, wpx, d_dt, coop_threshold, d_glt, td, 0.f, 0.f, 0.f, 0.f};

@@ -14,14 +14,16 @@ occ = wl.load_map("basement_hallways_5cm")
 omap = rl.PyOMap(np.ascontiguousarray(occ.T.astype(bool)))
 n, M = 4000, 60
 parts = torch.from_numpy(wl.pf_particles_uniform(occ, n, seed=3)).cuda()
+if len(sys.argv) > 1 and sys.argv[1] == "tracking":
+    parts = torch.from_numpy(wl.pf_particles_tracking(occ, n, seed=3)[0]).cuda()
 angles = torch.from_numpy(wl.lidar_angles(M)).cuda()
 obs = torch.from_numpy(np.linspace(5, 450, M).astype(np.float32)).cuda()
 w = torch.empty(n, dtype=torch.float64, device="cuda")
 stream = torch.cuda.current_stream()
-for mr in (0.5, 20.0, 100.0, 500.0):
+for mr in (0.5, 500.0):
     rm = rl.PyRayMarchingGPU(omap, mr)
     rm.set_sensor_model(wl.sensor_table(501))
-    for coop in (0, 3):
+    for coop in (0, 8, 16, 32):
         rm.set_coop_threshold(coop)
         side = torch.cuda.Stream()
         side.wait_stream(stream)

@@ -22,7 +22,7 @@ for N in (1 << 18, 1 << 22, 1 << 24, 1 << 26):
     out = torch.empty(N, dtype=torch.float32, device="cuda")
     for pv in (0, 1):
         rm.set_persistent(pv)
-        for coop in (0, 3):
+        for coop in (0, 12):
             rm.set_coop_threshold(coop)
             med, mn = timeit(lambda: rm.calc_range_many_grid(q, out))
             print("RM random N=%9d persist=%d coop=%d  %8.3f ms %7.2f G rays/s" % (N, pv, coop, med, N / med / 1e6))
@@ -37,7 +37,7 @@ for (n, M) in ((4000, 60), (100000, 60), (20000, 1080)):
         obs = torch.from_numpy(np.linspace(5, 450, M).astype(np.float32)).cuda()
         w = torch.empty(n, dtype=torch.float64, device="cuda")
         rng = torch.empty(n * M, dtype=torch.float32, device="cuda")
-        for coop in (0, 1, 2, 3, 4, 6, 8, 12):
+        for coop in (0, 2, 4, 6, 8, 12, 16, 24, 32):
             rm.set_coop_threshold(coop)
             med, mn = timeit(lambda: rm.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs, w), iters=20)
             med2, mn2 = timeit(lambda: rm.calc_range_repeat_angles(parts, angles, rng), iters=20)
