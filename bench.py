@@ -535,11 +535,15 @@ def extra_throughput(rl, wl, occ, omap, dev, stream, peak):
         n = 1 << 20
         q4 = torch.from_numpy(wl.random_queries(4096, 4096, n, seed=3)).to(dev)
         r4 = torch.empty(n, dtype=torch.float32, device=dev)
-        frames = [[(x0, y0, torch.from_numpy(p).to(dev)) for x0, y0, p in wl.flip_blocks(occ4, f, seed=2026)] for f in range(8)]
+        frames = []
+        for f in range(8):
+            blocks = wl.flip_blocks(occ4, f, seed=2026)
+            rects = np.array([[x0, y0, p.shape[0], p.shape[1]] for x0, y0, p in blocks], np.int32)
+            frames.append((torch.from_numpy(np.concatenate([p.ravel() for _, _, p in blocks])).to(dev), rects))
 
         def frame(f):
-            for x0, y0, p in frames[f % 8]:
-                bl.update_map(p, x0, y0)
+            patches, rects = frames[f % 8]
+            bl.update_map_batch(patches, rects)  # all 64 patches of the frame in one launch
             bl.calc_range_many_grid(q4, r4)
 
         for f in range(3):

@@ -89,6 +89,9 @@ int rl_method_synchronize(rl_method* m);
  * on it (BL: bit grid only; RM: distance transform rebuilt; CDDT: table rebuilt).
  * patch may be host or device memory. */
 int rl_method_update_map(rl_method* m, const uint8_t* patch_xmajor, int x0, int y0, int w, int h);
+/* the same for n non-overlapping patches in ONE launch: rects = n x (x0, y0, w, h) (HOST ints); the
+ * patches' bytes are concatenated in `patches` (HOST or DEVICE), each x-major inside its rectangle. */
+int rl_method_update_map_batch(rl_method* m, const uint8_t* patches_xmajor, const int* rects, int n);
 /* bytes of device memory held by the acceleration structure (RangeMethod::memory()) */
 int64_t rl_method_memory(const rl_method* m);
 

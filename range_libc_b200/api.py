@@ -230,6 +230,17 @@ class _RangeMethod:
             pp, sp = _buf(patch_xmajor, np.uint8, 2, "patch")
         check(lib().rl_method_update_map(self._h, pp, int(x0), int(y0), sp[0], sp[1]))
 
+    def update_map_batch(self, patches, rects):
+        """Dynamic maps: n non-overlapping patches in one launch.  rects: int32 [n, 4] (x0, y0, w, h) host array;
+        patches: uint8 1-D, the patches' bytes concatenated (numpy or torch CUDA tensor)."""
+        rects = np.ascontiguousarray(rects, dtype=np.int32)
+        if not _is_torch(patches):
+            patches = np.ascontiguousarray(patches, dtype=np.uint8)
+        pp, sp = _buf(patches, np.uint8, 1, "patches")
+        if rects.ndim != 2 or rects.shape[1] != 4 or int((rects[:, 2].astype(np.int64) * rects[:, 3]).sum()) != sp[0]:
+            raise ValueError("rects must be [n,4] and patches must hold sum(w*h) bytes")
+        check(lib().rl_method_update_map_batch(self._h, pp, C.c_void_p(rects.ctypes.data), rects.shape[0]))
+
     def memory(self):
         return int(lib().rl_method_memory(self._h))
 

@@ -33,6 +33,7 @@ SIGNATURES = {
     "rl_method_use_own_stream": (_i, [_vp]),
     "rl_method_synchronize": (_i, [_vp]),
     "rl_method_update_map": (_i, [_vp, _vp, _i, _i, _i, _i]),
+    "rl_method_update_map_batch": (_i, [_vp, _vp, _vp, _i]),
     "rl_method_memory": (C.c_int64, [_vp]),
     "rl_calc_range": (_i, [_vp, _f, _f, _f, C.POINTER(_f)]),
     "rl_calc_range_many": (_i, [_vp, _vp, _vp, _i]),

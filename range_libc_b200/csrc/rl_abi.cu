@@ -446,6 +446,51 @@ int rl_debug_set_persistent(rl_method* m, int on) {
   return RL_OK;
 }
 
+int rl_method_update_map_batch(rl_method* m, const uint8_t* patches, const int* rects, int n) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!patches || !rects))) {
+    set_error("rl_method_update_map_batch: bad arguments");
+    return RL_E_INVALID;
+  }
+  if (n == 0) return RL_OK;
+  std::vector<long long> offsets(n);
+  long long total = 0;
+  for (int p = 0; p < n; ++p) {
+    const int x0 = rects[4 * p], y0 = rects[4 * p + 1], w = rects[4 * p + 2], h = rects[4 * p + 3];
+    if (x0 < 0 || y0 < 0 || w <= 0 || h <= 0 || x0 + w > m->W || y0 + h > m->H) {
+      set_error("rl_method_update_map_batch: patch outside the map");
+      return RL_E_INVALID;
+    }
+    offsets[p] = total;
+    total += (long long)w * h;
+  }
+  // staging: [rects | offsets | patches (if on the host)]
+  const size_t b_rects = align256(sizeof(int) * 4 * (size_t)n), b_off = align256(sizeof(long long) * (size_t)n);
+  const bool dev_patches = is_device_ptr(patches);
+  rc = ensure_stage(m, b_rects + b_off + (dev_patches ? 0 : align256((size_t)total)));
+  if (rc) return rc;
+  char* base = (char*)m->d_stage;
+  RL_CUDA(cudaMemcpyAsync(base, rects, sizeof(int) * 4 * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+  RL_CUDA(cudaMemcpyAsync(base + b_rects, offsets.data(), sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+  const uint8_t* d_patches = patches;
+  if (!dev_patches) {
+    RL_CUDA(cudaMemcpyAsync(base + b_rects + b_off, patches, (size_t)total, cudaMemcpyHostToDevice, m->stream));
+    d_patches = (const uint8_t*)(base + b_rects + b_off);
+  }
+  rc = apply_patch_batch(m, d_patches, (const int*)base, (const long long*)(base + b_rects), n);
+  if (rc) return rc;
+  RL_CUDA(cudaStreamSynchronize(m->stream));  // `offsets` and the caller's host arrays are released on return
+  if (m->kind == RL_RM || m->kind == RL_GLT) rc = build_distance_transform(m);
+  if (!rc && m->kind == RL_GLT) rc = glt_build(m);
+  if (m->kind == RL_CDDT || m->kind == RL_PCDDT) {
+    const bool was_pruned = m->pruned;
+    rc = cddt_build(m);
+    if (!rc && was_pruned) rc = cddt_prune(m, m->max_range);
+  }
+  return rc;
+}
+
 int64_t rl_method_memory(const rl_method* m) {
   if (!m) return RL_E_INVALID;
   int64_t bytes = (int64_t)m->W * m->H + (int64_t)m->W * m->wpy * 4 + (int64_t)m->H * m->wpx * 4;

@@ -150,7 +150,7 @@ __device__ __forceinline__ float rm_march_block(const MapView& mv, float max_ran
     s_n = 0;
     s_next = 0;
   }
-  while (true) {
+  for (int bursts = 1;; ++bursts) {
     if (active) {
       int n = RL_BLOCK_BURST;
       bool done;
@@ -161,7 +161,8 @@ __device__ __forceinline__ float rm_march_block(const MapView& mv, float max_ran
     }
     const int alive = __syncthreads_count(active);
     if (alive == 0) return result;
-    if (alive <= handoff) break;
+    // few rays left -- or, after 24 steps, a moderate number of rays that are evidently long ones
+    if (alive <= handoff || (bursts >= 3 && alive <= 4 * handoff)) break;
   }
   if (active) {
     const int q = atomicAdd(&s_n, 1);

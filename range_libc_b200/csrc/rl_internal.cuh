@@ -187,6 +187,7 @@ int build_distance_transform(rl_method* m);
 // rl_occ.cu
 int upload_occupancy(rl_method* m, const rl_map* map);
 int apply_patch(rl_method* m, const uint8_t* d_patch, int x0, int y0, int w, int h);
+int apply_patch_batch(rl_method* m, const uint8_t* d_patches, const int* d_rects, const long long* d_offsets, int n);
 // rl_cddt.cu
 int cddt_build(rl_method* m);
 int cddt_prune(rl_method* m, float max_range);

@@ -55,6 +55,50 @@ __global__ void patch_kernel(uint8_t* __restrict__ occ, const uint8_t* __restric
   occ[(size_t)(x0 + px) * H + (y0 + py)] = patch[idx] ? 1 : 0;
 }
 
+// ---- batched patches (dynamic maps, BASELINE config 4): one CTA per patch, three phases in one launch ----
+// rects[4*p .. 4*p+3] = x0, y0, w, h; patch p's bytes start at offsets[p] in `patches` (x-major inside the patch)
+__global__ void patch_batch_kernel(uint8_t* __restrict__ occ, uint32_t* __restrict__ bits_y, uint32_t* __restrict__ bits_x,
+                                   const uint8_t* __restrict__ patches, const int* __restrict__ rects,
+                                   const long long* __restrict__ offsets, int W, int H, int wpy, int wpx) {
+  const int p = blockIdx.x;
+  const int x0 = rects[4 * p], y0 = rects[4 * p + 1], w = rects[4 * p + 2], h = rects[4 * p + 3];
+  const uint8_t* src = patches + offsets[p];
+  for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+    const int px = i / h, py = i - px * h;
+    occ[(size_t)(x0 + px) * H + (y0 + py)] = src[i] ? 1 : 0;
+  }
+  __syncthreads();  // the words below are rebuilt from occ; patches of one batch must not overlap
+  const int wb = y0 >> 5, we = ((y0 + h - 1) >> 5) + 1;
+  for (int i = threadIdx.x; i < w * (we - wb); i += blockDim.x) {
+    const int x = x0 + i / (we - wb), wd = wb + i % (we - wb);
+    uint32_t v = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int y = (wd << 5) + b;
+      if (y < H && occ[(size_t)x * H + y]) v |= (1u << b);
+    }
+    bits_y[(size_t)x * wpy + wd] = v;
+  }
+  const int xb = x0 >> 5, xe = ((x0 + w - 1) >> 5) + 1;
+  for (int i = threadIdx.x; i < h * (xe - xb); i += blockDim.x) {
+    const int y = y0 + i % h, wd = xb + i / h;
+    uint32_t v = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int x = (wd << 5) + b;
+      if (x < W && occ[(size_t)x * H + y]) v |= (1u << b);
+    }
+    bits_x[(size_t)y * wpx + wd] = v;
+  }
+}
+
+int apply_patch_batch(rl_method* m, const uint8_t* d_patches, const int* d_rects, const long long* d_offsets, int n) {
+  if (n <= 0) return RL_OK;
+  patch_batch_kernel<<<n, 256, 0, m->stream>>>(m->d_occ, m->d_bits_y, m->d_bits_x, d_patches, d_rects, d_offsets, m->W,
+                                               m->H, m->wpy, m->wpx);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
+}
+
 int upload_occupancy(rl_method* m, const rl_map* map) {
   const size_t n = (size_t)m->W * m->H;
   m->wpy = (m->H + 31) / 32;

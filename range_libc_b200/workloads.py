@@ -76,14 +76,17 @@ def synthetic_map(size, seed=2026, n_segments=None, n_discs=None):
 
 
 def flip_blocks(occ, frame, seed=2026, n_blocks=64, block=16):
-    """Per-frame occupancy update for the dynamic-map config (C4): toggles n_blocks seeded
-    block x block patches.  Returns list of (x0, y0, patch uint8 [block, block]) and applies them."""
+    """Per-frame occupancy update for the dynamic-map config (C4): toggles n_blocks seeded, block-aligned
+    (hence non-overlapping) block x block patches.  Returns list of (x0, y0, patch uint8 [block, block]) and
+    applies them to `occ`."""
     rng = np.random.default_rng(seed * 1000003 + frame)
     W, H = occ.shape
+    gx, gy = (W - 2) // block, (H - 2) // block
+    picks = rng.choice(gx * gy, size=min(n_blocks, gx * gy), replace=False)
     out = []
-    for _ in range(n_blocks):
-        x0 = int(rng.integers(1, W - block - 1))
-        y0 = int(rng.integers(1, H - block - 1))
+    for k in picks:
+        x0 = 1 + int(k // gy) * block
+        y0 = 1 + int(k % gy) * block
         patch = (1 - occ[x0:x0 + block, y0:y0 + block]).astype(np.uint8)
         occ[x0:x0 + block, y0:y0 + block] = patch
         out.append((x0, y0, np.ascontiguousarray(patch)))

@@ -179,6 +179,25 @@ def test_dynamic_map_update_bl():
         assert_bit_equal(out, port.Oracle(port.BL, occ, MR, threads=8).calc_range_many(q), "frame %d" % frame)
 
 
+def test_dynamic_map_update_batched():
+    import torch
+    q = wl.random_queries(1024, 1024, 50000, seed=14)
+    for kn, kind in (("bl", port.BL), ("rm", port.RM)):
+        occ = wl.synthetic_map(1024, seed=13)
+        meth = make(kn, occ)
+        for frame in range(2):
+            blocks = wl.flip_blocks(occ, frame, seed=13, n_blocks=24, block=16)  # block aligned: no overlaps
+            rects = np.array([[x0, y0, 16, 16] for x0, y0, _ in blocks], np.int32)
+            flat = np.concatenate([p.ravel() for _, _, p in blocks])
+            if frame == 0:
+                meth.update_map_batch(flat, rects)  # host patches
+            else:
+                meth.update_map_batch(torch.from_numpy(flat).cuda(), rects)  # device patches
+            out = np.empty(len(q), np.float32)
+            meth.calc_range_many_grid(q, out)
+            assert_bit_equal(out, port.Oracle(kind, occ, MR, threads=8).calc_range_many(q), "%s frame %d" % (kn, frame))
+
+
 def test_dynamic_map_update_rm_and_cddt():
     occ = wl.synthetic_map(512, seed=21)
     q = wl.random_queries(512, 512, 20000, seed=22)
