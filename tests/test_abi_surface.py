@@ -80,3 +80,21 @@ def test_png_ingest_equals_reference_loader():
             continue
         thr = 1 if "synthetic.map" in f else 128
         assert np.array_equal(ref.RefMap(png=f, threshold=thr).occ(), mapio.load_png(f, thr)), f
+
+
+def test_cpp_header_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """include/rangelib_b200.hpp (C++ mirror of ranges::RangeMethod & co.) builds against the library; without a
+    GPU constructing a method throws (exit code 3), with one it casts rays (exit code 0)."""
+    import shutil
+    import subprocess
+    import torch
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "hpp_smoke")
+    libdir = os.path.dirname(cabi.LIB_PATH)
+    subprocess.check_call([gxx, "-std=c++14", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "hpp_smoke.cpp"), "-o", exe, "-L", libdir,
+                           "-lrangelib_b200", "-Wl,-rpath," + libdir])
+    rc = subprocess.run([exe], capture_output=True, text=True)
+    assert rc.returncode == (0 if torch.cuda.is_available() else 3), rc.stdout + rc.stderr

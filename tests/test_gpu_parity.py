@@ -387,3 +387,60 @@ def test_giant_lut_cast_gpu():
     glt.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs, w)
     assert_bit_equal(w, o.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs), "glt fused")
     assert glt.memory() >= W * H * td * 2
+
+
+def test_cpp_header_mirror_on_gpu(tmp_path):
+    from test_abi_surface import test_cpp_header_mirror_compiles_and_fails_loudly_without_gpu as run
+    run(tmp_path)
+
+
+@pytest.mark.parametrize("kn", ["bl", "rm", "cddt", "pcddt"])
+def test_rotated_world_fused_and_odd_parameters(kn):
+    """Rotated ROS world frame through the angle-fan and fused entry points, a non-integer max_range, a sensor
+    table whose width is not max_range + 1 (clamping), observations beyond the table, odd theta_discretization."""
+    occ = wl.load_map("basement_fixed_rectangle")
+    W, H = occ.shape
+    ang = 0.4
+    world = (0.07, ang, 1.5, -2.5, float(np.sin(ang)), float(np.cos(ang)))
+    mr, td, K = 123.45, 7, 100
+    meth = make(kn, occ, max_range=mr, td=td, world=world)
+    o = port.Oracle(KINDS[kn], occ, mr, td, threads=4)
+    o.set_world(*world)
+    parts = wl.grid_to_world(wl.random_queries(W, H, 700, seed=61), world[0], world[2], world[3], ang)
+    angles = wl.lidar_angles(33, fov=2.0)
+    obs = np.linspace(-1.0, 12.0, 33).astype(np.float32)  # world units: up to 171 px >> K-1
+    table = wl.sensor_table(K)
+    meth.set_sensor_model(table)
+    o.set_sensor_model(table)
+    out = np.empty(len(parts) * len(angles), np.float32)
+    meth.calc_range_repeat_angles(parts, angles, out)
+    ref_ranges = o.numpy_calc_range_angles(parts, angles)
+    assert_bit_equal(out, ref_ranges, kn + " angles")
+    w = np.empty(len(parts), np.float64)
+    meth.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs, w)
+    assert_bit_equal(w, o.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs), kn + " fused")
+    w2 = np.empty(len(parts), np.float64)
+    meth.eval_sensor_model(obs, out, w2, len(angles), len(parts))
+    assert_bit_equal(w2, o.eval_sensor_model(obs, ref_ranges, len(angles), len(parts)), kn + " two-step")
+
+
+@pytest.mark.parametrize("name", ["quad.map", "single_pixel.map", "small.map"])
+def test_degenerate_maps_all_kinds(name):
+    occ = wl.load_map(name)
+    W, H = occ.shape
+    q = wl.random_queries(W, H, 2000, seed=71)
+    q[:200, :2] = np.random.default_rng(1).uniform(-3, max(W, H) + 3, (200, 2))  # also outside the map
+    for kn in ("bl", "rm"):
+        out = np.empty(len(q), np.float32)
+        make(kn, occ).calc_range_many_grid(q, out)
+        assert_bit_equal(out, port.Oracle(KINDS[kn], occ, MR).calc_range_many(q), "%s %s" % (name, kn))
+    qi = q[200:]  # CDDT reads map.grid[x][y] unchecked in the reference: in-map queries only
+    for kn in ("cddt", "pcddt"):
+        out = np.empty(len(qi), np.float32)
+        make(kn, occ).calc_range_many_grid(qi, out)
+        assert_bit_equal(out, port.Oracle(KINDS[kn], occ, MR, TD).calc_range_many(qi), "%s %s" % (name, kn))
+    m = rl.PyOMap(np.ascontiguousarray(occ.T.astype(bool)))
+    glt = rl.PyGiantLUTCast(m, MR, 12)
+    out = np.empty(len(q), np.float32)
+    glt.calc_range_many_grid(q, out)
+    assert_bit_equal(out, port.Oracle(port.GLT, occ, MR, 12).calc_range_many(q), "%s glt" % name)
