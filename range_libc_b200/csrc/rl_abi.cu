@@ -244,7 +244,6 @@ static void free_method(rl_method* m) {
   cudaFree(m->d_epoch);
   cudaFree(m->d_counter);
   if (m->h_stage) cudaFreeHost(m->h_stage);
-  if (m->ev) cudaEventDestroy(m->ev);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
 }

@@ -123,7 +123,6 @@ struct rl_method {
   unsigned td = 0;
   rl::WorldXform xf{};
   cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaEvent_t ev = nullptr;
 
   // occupancy on device
   uint8_t* d_occ = nullptr;
