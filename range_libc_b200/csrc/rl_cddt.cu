@@ -326,10 +326,13 @@ int cddt_build(rl_method* m) {
   RL_CUDA(sc.alloc(&d_flags, (size_t)cells));
   RL_CUDA(sc.alloc(&d_edge, (size_t)cells));
   RL_CUDA(sc.alloc(&d_nedge, 1));
-  edge_flags_kernel<<<blocks_for(cells, 256), 256, 0, st>>>(m->d_occ, W, H, d_flags);
-  count_launch();
-  RL_CHECK_LAUNCH();
-  {
+  if (cells > 0) {
+    edge_flags_kernel<<<blocks_for(cells, 256), 256, 0, st>>>(m->d_occ, W, H, d_flags);
+    count_launch();
+    RL_CHECK_LAUNCH();
+  }
+  RL_CUDA(cudaMemsetAsync(d_nedge, 0, sizeof(long long), st));
+  if (cells > 0) {
     size_t tb = 0;
     cub::CountingInputIterator<long long> it(0);
     RL_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, it, d_flags, d_edge, d_nedge, cells, st));

@@ -106,12 +106,14 @@ int upload_occupancy(rl_method* m, const rl_map* map) {
   m->wpx = (m->W + 31) / 32;
   RL_CUDA(cudaMalloc(&m->d_bits_y, sizeof(uint32_t) * (size_t)m->W * m->wpy + 4));
   RL_CUDA(cudaMalloc(&m->d_bits_x, sizeof(uint32_t) * (size_t)m->H * m->wpx + 4));
-  RL_CUDA(cudaMemcpyAsync(m->d_occ, map->occ.data(), n, cudaMemcpyHostToDevice, m->stream));
+  if (n) RL_CUDA(cudaMemcpyAsync(m->d_occ, map->occ.data(), n, cudaMemcpyHostToDevice, m->stream));
   const long long total = (long long)m->W * m->wpy;
-  pack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_y, m->W, m->H, m->wpy, 0,
-                                                                          m->W, 0, m->wpy);
-  count_launch();
-  RL_CHECK_LAUNCH();
+  if (total > 0) {
+    pack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_y, m->W, m->H, m->wpy,
+                                                                            0, m->W, 0, m->wpy);
+    count_launch();
+    RL_CHECK_LAUNCH();
+  }
   const long long total_x = (long long)m->H * m->wpx;
   if (total_x > 0) {
     pack_bits_x_kernel<<<(unsigned)((total_x + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_x, m->W, m->H,

@@ -444,3 +444,24 @@ def test_degenerate_maps_all_kinds(name):
     out = np.empty(len(q), np.float32)
     glt.calc_range_many_grid(q, out)
     assert_bit_equal(out, port.Oracle(port.GLT, occ, MR, 12).calc_range_many(q), "%s glt" % name)
+
+
+def test_empty_map_and_empty_batches():
+    """Zero-sized maps and batches are legal inputs: every ray of an empty map leaves it at once."""
+    q = np.array([[0.5, 0.5, 0.1], [3.0, -2.0, 2.0]], np.float32)
+    for shape in ((0, 0), (0, 5), (7, 0)):
+        m = rl.PyOMap(np.zeros(shape, bool))
+        for ctor in (lambda: rl.PyRayMarchingGPU(m, 50.0), lambda: rl.PyBresenhamsLine(m, 50.0),
+                     lambda: rl.PyCDDTCast(m, 50.0, 12), lambda: rl.PyGiantLUTCast(m, 50.0, 12)):
+            meth = ctor()
+            out = np.full(2, -1.0, np.float32)
+            meth.calc_range_many_grid(q, out)
+            assert (out == 50.0).all(), (shape, type(meth).__name__, out)
+            meth.calc_range_many_grid(np.zeros((0, 3), np.float32), np.zeros(0, np.float32))
+    occ = wl.load_map("small.map")
+    meth = make("pcddt", occ)
+    meth.set_sensor_model(wl.sensor_table(64))
+    meth.calc_range_repeat_angles(np.zeros((0, 3), np.float32), np.zeros(4, np.float32), np.zeros(0, np.float32))
+    w = np.zeros(0, np.float64)
+    meth.calc_range_repeat_angles_eval_sensor_model(np.zeros((0, 3), np.float32), np.zeros(4, np.float32),
+                                                    np.zeros(4, np.float32), w)
