@@ -235,8 +235,7 @@ static void free_method(rl_method* m) {
   cudaSetDevice(m->device);
   cddt_free(m);
   cudaFree(m->d_occ);
-  cudaFree(m->d_bits_y);
-  cudaFree(m->d_bits_x);
+  cudaFree(m->d_bits_t);
   cudaFree(m->d_dt);
   cudaFree(m->d_glt);
   cudaFree(m->d_table);
@@ -492,7 +491,7 @@ int rl_method_update_map_batch(rl_method* m, const uint8_t* patches, const int* 
 
 int64_t rl_method_memory(const rl_method* m) {
   if (!m) return RL_E_INVALID;
-  int64_t bytes = (int64_t)m->W * m->H + (int64_t)m->W * m->wpy * 4 + (int64_t)m->H * m->wpx * 4;
+  int64_t bytes = (int64_t)m->W * m->H + (int64_t)m->tiles8_x() * m->tiles8_y() * 8;
   if (m->kind == RL_RM || m->kind == RL_GLT) bytes += (int64_t)m->dt_elems() * 4;
   if (m->kind == RL_GLT) bytes += (int64_t)m->W * m->H * m->td * 2;
   if (m->kind == RL_CDDT || m->kind == RL_PCDDT) bytes += m->nvalues * 4 + (m->nbins + 1) * 8 + (int64_t)m->td * 16;

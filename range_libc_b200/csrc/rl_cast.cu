@@ -16,6 +16,8 @@
 //   eval_sensor_kernel        RangeMethod::eval_sensor_model              RangeLib.h:533-555
 //
 // KIND: RL_BL (:696-769), RL_RM (:927-962), RL_CDDT / RL_PCDDT (:1342-1516), RL_GLT (:1869-1880).
+#include <cstdlib>
+
 #include "rl_internal.cuh"
 #include "rl_math.cuh"
 
@@ -211,17 +213,17 @@ __device__ __forceinline__ float rm_cast(const MapView& mv, float max_range, flo
 
 __device__ __forceinline__ bool occ_at(const MapView& mv, int x, int y) {  // OMap::isOccupied :204-210
   if ((unsigned)x >= (unsigned)mv.W || (unsigned)y >= (unsigned)mv.H) return false;
-  return (__ldg(mv.bits_y + (size_t)x * mv.wpy + (y >> 5)) >> (y & 31)) & 1u;
+  return (__ldg(mv.bits_t + (size_t)(x >> 3) * mv.tiles8_y + (y >> 3)) >> ((x & 7) * 8 + (y & 7))) & 1ULL;
 }
 
 // BresenhamsLine::calc_range, RangeLib.h:696-769.  All state is float, as in the reference; the
 // walk is the reference's recurrence (_x += +-1, error += deltay, conditional _y += +-1) step for
 // step, so the visited cells and the returned distance are bit-identical.  What differs is how a
 // step is evaluated:
-//  * cell test = one bit of a register-cached 32-cell word.  The grid is kept bit-packed along BOTH
-//    axes; a ray reads the copy packed along its major axis, so 32 consecutive steps share one
-//    word and a new word is loaded only when the minor coordinate changes or the word is used up
-//    (~270 cell tests per ray cost ~15 loads);
+//  * cell test = one bit of a register-cached 64-bit word holding an 8x8-cell tile of the map; a walk
+//    crosses a tile in ~8-11 steps whatever its direction, so ~270 cell tests per ray cost ~30 loads
+//    (bit-packing along one axis needed a load on almost every step of a diagonal walk, and the kernel
+//    was bound by L2 sector traffic: ncu, profiles/);
 //  * the float bounds tests `0 <= v && v < limit` (:755/:761) become one unsigned compare of
 //    floor(v) -- identical for every finite v -- and floor(v) is also the cell index;
 //  * the loop test `(int)_x != (int)(x1 + xstep)` becomes an interval test on _x (trunc(v) == T is an
@@ -231,10 +233,10 @@ __device__ __forceinline__ bool occ_at(const MapView& mv, int x, int y) {  // OM
 //    any more and the result (max_range) is returned at once.
 struct BlState {
   float _x, _y, error, deltax, deltay, xstep, ystep, lo, hi, x0, y0;
-  int cur_wi;
-  uint32_t cur;
-  int guard;
-  bool steep;
+  float stop_u;  // the walk is over (or has jumped its target) once xstep * _x >= stop_u
+  int cur_tile;
+  unsigned long long cur;
+  bool steep, skipped;
 };
 
 // everything before the walk (:698-745).  Returns true when the result is already known.
@@ -269,21 +271,18 @@ __device__ __forceinline__ bool bl_setup(const MapView& mv, float max_range, flo
   else if (target < 0) { st.lo = nextafterf((float)target - 1.0f, 0.0f); st.hi = nextafterf((float)target, 0.0f); }
   else { st.lo = nextafterf(-1.0f, 0.0f); st.hi = 1.0f; }
   if (target == INT_MIN || fabsf(x0) > 8388608.0f || fabsf(x1) > 8388608.0f) return true;  // far outside any map
-  st.cur_wi = -1;
+  st.cur_tile = -1;
   st.cur = 0;
-  // Normally the walk takes deltax + 1..3 steps.  The reference's `_x += xstep` is a float accumulation:
-  // when _x crosses a power of two with low fraction bits set, the sum rounds and (int)_x can jump over
-  // the target, after which the reference keeps walking (and hangs once the walk is outside the map).
-  // We follow it for as long as a cell can still be hit; the "left the map for good" test in bl_step
-  // ends such walks with max_range.  The counter is only a backstop.
-  st.guard = f2i(max_range) + mv.W + mv.H + 16;
+  st.skipped = false;
+  // _x moves monotonically by xstep, so "trunc(_x) == target for the first time" is a one-sided test on
+  // u = xstep * _x (exact: a sign flip): u >= lo when walking up, u > -hi when walking down.
+  st.stop_u = (st.xstep > 0.0f) ? st.lo : nextafterf(-st.hi, INFINITY);
   return st._x >= st.lo && st._x < st.hi;  // zero-length walk
 }
 
 // one iteration of the walk (:745-767).  Returns true when the ray has ended.
 __device__ __forceinline__ bool bl_step(const MapView& mv, float max_range, BlState& st, float* result) {
   *result = max_range;
-  if (--st.guard < 0) return true;
   st._x = fadd(st._x, st.xstep);
   st.error = fadd(st.error, st.deltay);
   if (fmul(st.error, 2.0f) >= st.deltax) {  // (double)error*2.0 >= (double)deltax: doubling is exact
@@ -295,12 +294,13 @@ __device__ __forceinline__ bool bl_step(const MapView& mv, float max_range, BlSt
   const unsigned lim_b = st.steep ? (unsigned)mv.H : (unsigned)mv.W;  // minor coordinate _y
   const int a = __float2int_rd(st._x), b = __float2int_rd(st._y);
   if ((unsigned)a < lim_a && (unsigned)b < lim_b) {
-    const int wi = b * (st.steep ? mv.wpx : mv.wpy) + (a >> 5);
-    if (wi != st.cur_wi) {
-      st.cur_wi = wi;
-      st.cur = __ldg((st.steep ? mv.bits_x : mv.bits_y) + wi);  // the copy packed along the major axis
+    const int cx = st.steep ? a : b, cy = st.steep ? b : a;  // map cell
+    const int tile = (cx >> 3) * mv.tiles8_y + (cy >> 3);
+    if (tile != st.cur_tile) {
+      st.cur_tile = tile;
+      st.cur = __ldg(mv.bits_t + tile);
     }
-    if ((st.cur >> (a & 31)) & 1u) {
+    if ((st.cur >> ((cx & 7) * 8 + (cy & 7))) & 1ULL) {
       const float xd = fsub(st._x, st.x0), yd = fsub(st._y, st.y0);
       *result = __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
       return true;
@@ -310,7 +310,17 @@ __device__ __forceinline__ bool bl_step(const MapView& mv, float max_range, BlSt
     if ((st.xstep > 0.0f) ? (a >= (int)lim_a) : (a < 0)) return true;
     if ((st.ystep > 0.0f) ? (b >= (int)lim_b) : (b < 0)) return true;
   }
-  return st._x >= st.lo && st._x < st.hi;
+  if (fmul(st.xstep, st._x) >= st.stop_u) {
+    // Normally this is the end of the walk (trunc(_x) == target).  The reference's `_x += xstep` is a float
+    // accumulation, though: when _x crosses a power of two with low fraction bits set the sum rounds and
+    // (int)_x can jump over the target, after which the reference keeps walking (and never returns once the
+    // walk is outside the map).  We follow it for as long as a cell can still be hit -- the "left the map
+    // for good" test above ends such walks -- with a backstop one map diagonal further on.
+    if (st.skipped || (st._x >= st.lo && st._x < st.hi)) return true;
+    st.skipped = true;
+    st.stop_u = fadd(fmul(st.xstep, st._x), (float)(mv.W + mv.H) + max_range);
+  }
+  return false;
 }
 
 __device__ __forceinline__ float bl_cast(const MapView& mv, float max_range, float x, float y, float heading) {
@@ -656,6 +666,67 @@ __global__ void sincosf_kernel(const float* x, float* s, float* c, int n) {
 }
 
 // ------------------------------------------------------------------------------------------
+// BL, large independent batches: persistent warps with lane re-queuing.  A Bresenham walk takes
+// anything from 1 to ~500 steps (it stops at the first obstacle or at the map border); with one
+// ray per thread ncu shows 10.9 of 32 threads active per instruction on an instruction-issue
+// bound kernel (87 % issue slots busy; profiles/ncu_bl_r01.txt).  Here a warp owns a chunk of
+// rays; the lanes walk in bursts of RL_BL_BURST steps, and between bursts the lanes whose walk
+// has ended are handed the next rays of the chunk (their set-up -- bounds test, sin/cos, deltas,
+// ~120 instructions -- runs for those lanes only, so it waits until RL_BL_REFILL lanes are idle).
+// ------------------------------------------------------------------------------------------
+#define RL_BL_REFILL 4
+#define RL_BL_BURST 32
+template <int MODE>
+__global__ void __launch_bounds__(256, 5)
+bl_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __restrict__ ins,
+                  const float* __restrict__ angles, float* __restrict__ outs, long long total, int M, int chunk,
+                  int refill_at, int burst_len) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long begin = warp_global * chunk;
+  const long long end = min(begin + (long long)chunk, total);
+  if (begin >= end) return;
+  const int count = (int)(end - begin);
+  int next = 0;  // next ray of the chunk to hand out (warp-uniform)
+  bool active = false;
+  int id = 0;
+  BlState st;
+  while (true) {
+    const unsigned idle = __ballot_sync(FULL, !active);
+    const int n_idle = __popc(idle);
+    if (next < count && (n_idle >= refill_at || n_idle == 32)) {
+      const int rank = __popc(idle & ((1u << lane) - 1u));
+      if (!active && next + rank < count) {
+        id = next + rank;
+        float gx, gy, gth, result;
+        load_pose<MODE>(xf, ins, angles, begin + id, M, &gx, &gy, &gth);
+        if (bl_setup(mv, max_range, gx, gy, gth, st, &result)) {
+          outs[begin + id] = (MODE == MODE_GRID) ? result : fmul(result, xf.scale);
+        } else {
+          active = true;
+        }
+      }
+      next = min(count, next + n_idle);
+      continue;  // lanes whose new ray ended during set-up are refilled before stepping
+    }
+    if (n_idle == 32) break;  // nothing left to hand out and nobody walking
+    if (active) {
+      float result;
+      bool done;
+      int burst = burst_len;
+      do {
+        done = bl_step(mv, max_range, st, &result);
+      } while (!done && --burst);
+      if (done) {
+        outs[begin + id] = (MODE == MODE_GRID) ? result : fmul(result, xf.scale);
+        active = false;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // RM, large independent batches: persistent warps with lane re-queuing.
 //
 // Sphere tracing needs 2..300 dependent distance-map reads per ray (mean ~6.5 on the basement
@@ -807,6 +878,24 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     const long long total = (mode == MODE_ANGLES) ? (long long)n * M : (long long)n;
     // RM with enough rays to give every resident warp more than one ray per lane: persistent
     // warps with lane re-queuing.  (max_range <= 0 never enters the marching loop.)
+    if (KIND == RL_BL && total >= (long long)sm_count() * 40 * 64 && m->persist) {
+      const long long rw = (long long)sm_count() * 40;
+      static const int bl_refill = getenv("RL_BL_REFILL") ? atoi(getenv("RL_BL_REFILL")) : RL_BL_REFILL;
+      static const int bl_burst = getenv("RL_BL_BURST") ? atoi(getenv("RL_BL_BURST")) : RL_BL_BURST;
+      long long per_warp = (total + rw - 1) / rw;
+      const int chunk = (int)min((long long)1 << 20, ((per_warp + 31) / 32) * 32);
+      const long long warps = (total + chunk - 1) / chunk;
+      const int grid = (int)((warps + 7) / 8);
+      if (mode == MODE_GRID)
+        bl_persist_kernel<MODE_GRID><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, bl_refill, bl_burst);
+      else if (mode == MODE_WORLD)
+        bl_persist_kernel<MODE_WORLD><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, bl_refill, bl_burst);
+      else
+        bl_persist_kernel<MODE_ANGLES><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, bl_refill, bl_burst);
+      count_launch();
+      RL_CHECK_LAUNCH();
+      return RL_OK;
+    }
     const long long resident_warps = (long long)sm_count() * 48;
     if (KIND == RL_RM && m->max_range > 0.0f && total >= resident_warps * 64 && m->persist) {
       long long per_warp = (total + resident_warps - 1) / resident_warps;

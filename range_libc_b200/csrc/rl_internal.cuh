@@ -53,10 +53,11 @@ __host__ __device__ __forceinline__ unsigned dt_index(int px, int py, int H) {
 struct MapView {
   int W, H;
   const uint8_t* occ;      // x-major bytes occ[x*H+y]
-  const uint32_t* bits_y;  // bit grid packed along y: word (x, y>>5), bit y&31; row stride wpy words
-  int wpy;
-  const uint32_t* bits_x;  // the same grid packed along x: word (y, x>>5), bit x&31; row stride wpx words
-  int wpx;
+  // occupancy bits in 8x8-cell tiles, one 64-bit word per tile: tile (x>>3, y>>3) at index
+  // (x>>3)*tiles8_y + (y>>3), bit (x&7)*8 + (y&7).  A Bresenham walk crosses a tile in ~8-11 steps
+  // whatever its direction, so one load serves that many cell tests.
+  const unsigned long long* bits_t;
+  int tiles8_y;
   const float* dt;         // float distance transform (RM), x-major, see dt_index
   int coop_threshold;      // RM: a CTA with at most this many live rays finishes them cooperatively, one per warp (0 = off)
   // GiantLUTCast (RangeLib.h:1772-1904): uint16 range per (x, y, theta bin), glt[(x*H + y)*td + i]
@@ -126,10 +127,9 @@ struct rl_method {
 
   // occupancy on device
   uint8_t* d_occ = nullptr;
-  uint32_t* d_bits_y = nullptr;
-  int wpy = 0;
-  uint32_t* d_bits_x = nullptr;
-  int wpx = 0;
+  unsigned long long* d_bits_t = nullptr;
+  int tiles8_x() const { return (W + 7) >> 3; }
+  int tiles8_y() const { return (H + 7) >> 3; }
   // RM
   float* d_dt = nullptr;
   // GiantLUT
@@ -165,7 +165,7 @@ struct rl_method {
   int coop_threshold = 16;
   int persist = 1;  // RM large batches: 0 one ray per thread, 1 persistent warps with lane re-queuing
   rl::MapView map_view() const {
-    rl::MapView v{W, H, d_occ, d_bits_y, wpy, d_bits_x, wpx, d_dt, coop_threshold, d_glt, td, 0.f, 0.f, 0.f, 0.f};
+    rl::MapView v{W, H, d_occ, d_bits_t, tiles8_y(), d_dt, coop_threshold, d_glt, td, 0.f, 0.f, 0.f, 0.f};
     if (kind == RL_GLT && td) {
       v.glt_td_div_2pi = (float)((double)td / RL_M_2PI);
       v.glt_twopi_div_td = (float)(RL_M_2PI / (double)((float)td));

@@ -1,50 +1,29 @@
 // Occupancy grid residency: byte grid (x-major, the reference's OMap::grid[x][y] order,
-// RangeLib.h:126) plus a bit-packed copy (32 cells of one x-column per word) that the BL walk
-// and the CDDT/BL "standing on an obstacle" test read.  Dynamic maps (BASELINE config 4)
+// RangeLib.h:126) plus a bit-packed copy in 8x8-cell tiles (one 64-bit word per tile) that the BL
+// walk and the CDDT/BL "standing on an obstacle" test read.  Dynamic maps (BASELINE config 4)
 // patch both on the device.
 #include "rl_internal.cuh"
 
 namespace rl {
 
-// one thread per output word
-__global__ void pack_bits_kernel(const uint8_t* __restrict__ occ, uint32_t* __restrict__ bits, int W, int H, int wpy,
-                                 int x_begin, int x_end, int word_begin, int word_end) {
-  const int nw = word_end - word_begin;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)(x_end - x_begin) * nw;
-  if (idx >= total) return;
-  const int x = x_begin + (int)(idx / nw);
-  const int wd = word_begin + (int)(idx % nw);
-  const int y0 = wd << 5;
-  uint32_t v = 0;
-  const uint8_t* col = occ + (size_t)x * H;
-#pragma unroll 4
-  for (int b = 0; b < 32; ++b) {
-    int y = y0 + b;
-    if (y < H && col[y]) v |= (1u << b);
+// one thread per 8x8 tile in the tile range [tx0, tx1) x [ty0, ty1)
+__global__ void pack_tiles_kernel(const uint8_t* __restrict__ occ, unsigned long long* __restrict__ bits, int W, int H,
+                                  int tiles_y, int tx0, int tx1, int ty0, int ty1) {
+  const int nty = ty1 - ty0;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)(tx1 - tx0) * nty) return;
+  const int tx = tx0 + (int)(idx / nty), ty = ty0 + (int)(idx % nty);
+  unsigned long long v = 0;
+  for (int i = 0; i < 8; ++i) {
+    const int x = (tx << 3) + i;
+    if (x >= W) break;
+    const uint8_t* col = occ + (size_t)x * H;
+    for (int j = 0; j < 8; ++j) {
+      const int y = (ty << 3) + j;
+      if (y < H && col[y]) v |= 1ULL << (i * 8 + j);
+    }
   }
-  bits[(size_t)x * wpy + wd] = v;
-}
-
-// x-packed copy: one thread per output word (y, x>>5)
-__global__ void pack_bits_x_kernel(const uint8_t* __restrict__ occ, uint32_t* __restrict__ bits, int W, int H, int wpx,
-                                   int y_begin, int y_end, int word_begin, int word_end) {
-  const int nw = word_end - word_begin;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)(y_end - y_begin) * nw;
-  if (idx >= total) return;
-  // consecutive threads take consecutive y so the byte reads of a warp are contiguous
-  const int ny = y_end - y_begin;
-  const int y = y_begin + (int)(idx % ny);
-  const int wd = word_begin + (int)(idx / ny);
-  const int x0 = wd << 5;
-  uint32_t v = 0;
-#pragma unroll 4
-  for (int b = 0; b < 32; ++b) {
-    int x = x0 + b;
-    if (x < W && occ[(size_t)x * H + y]) v |= (1u << b);
-  }
-  bits[(size_t)y * wpx + wd] = v;
+  bits[(size_t)tx * tiles_y + ty] = v;
 }
 
 __global__ void patch_kernel(uint8_t* __restrict__ occ, const uint8_t* __restrict__ patch, int H, int x0, int y0, int w,
@@ -55,11 +34,13 @@ __global__ void patch_kernel(uint8_t* __restrict__ occ, const uint8_t* __restric
   occ[(size_t)(x0 + px) * H + (y0 + py)] = patch[idx] ? 1 : 0;
 }
 
-// ---- batched patches (dynamic maps, BASELINE config 4): one CTA per patch, three phases in one launch ----
-// rects[4*p .. 4*p+3] = x0, y0, w, h; patch p's bytes start at offsets[p] in `patches` (x-major inside the patch)
-__global__ void patch_batch_kernel(uint8_t* __restrict__ occ, uint32_t* __restrict__ bits_y, uint32_t* __restrict__ bits_x,
+// ---- batched patches (dynamic maps, BASELINE config 4): one CTA per patch, two phases in one launch ----
+// rects[4*p .. 4*p+3] = x0, y0, w, h; patch p's bytes start at offsets[p] in `patches` (x-major inside the patch).
+// Patches of one batch must not share an 8x8 tile (block-aligned 16x16 patches never do) -- otherwise two CTAs
+// would rebuild the same tile word while one of them is still writing cells.
+__global__ void patch_batch_kernel(uint8_t* __restrict__ occ, unsigned long long* __restrict__ bits,
                                    const uint8_t* __restrict__ patches, const int* __restrict__ rects,
-                                   const long long* __restrict__ offsets, int W, int H, int wpy, int wpx) {
+                                   const long long* __restrict__ offsets, int W, int H, int tiles_y) {
   const int p = blockIdx.x;
   const int x0 = rects[4 * p], y0 = rects[4 * p + 1], w = rects[4 * p + 2], h = rects[4 * p + 3];
   const uint8_t* src = patches + offsets[p];
@@ -67,33 +48,28 @@ __global__ void patch_batch_kernel(uint8_t* __restrict__ occ, uint32_t* __restri
     const int px = i / h, py = i - px * h;
     occ[(size_t)(x0 + px) * H + (y0 + py)] = src[i] ? 1 : 0;
   }
-  __syncthreads();  // the words below are rebuilt from occ; patches of one batch must not overlap
-  const int wb = y0 >> 5, we = ((y0 + h - 1) >> 5) + 1;
-  for (int i = threadIdx.x; i < w * (we - wb); i += blockDim.x) {
-    const int x = x0 + i / (we - wb), wd = wb + i % (we - wb);
-    uint32_t v = 0;
-    for (int b = 0; b < 32; ++b) {
-      const int y = (wd << 5) + b;
-      if (y < H && occ[(size_t)x * H + y]) v |= (1u << b);
+  __syncthreads();
+  const int tx0 = x0 >> 3, tx1 = ((x0 + w - 1) >> 3) + 1, ty0 = y0 >> 3, ty1 = ((y0 + h - 1) >> 3) + 1;
+  const int nty = ty1 - ty0;
+  for (int t = threadIdx.x; t < (tx1 - tx0) * nty; t += blockDim.x) {
+    const int tx = tx0 + t / nty, ty = ty0 + t % nty;
+    unsigned long long v = 0;
+    for (int i = 0; i < 8; ++i) {
+      const int x = (tx << 3) + i;
+      if (x >= W) break;
+      for (int j = 0; j < 8; ++j) {
+        const int y = (ty << 3) + j;
+        if (y < H && occ[(size_t)x * H + y]) v |= 1ULL << (i * 8 + j);
+      }
     }
-    bits_y[(size_t)x * wpy + wd] = v;
-  }
-  const int xb = x0 >> 5, xe = ((x0 + w - 1) >> 5) + 1;
-  for (int i = threadIdx.x; i < h * (xe - xb); i += blockDim.x) {
-    const int y = y0 + i % h, wd = xb + i / h;
-    uint32_t v = 0;
-    for (int b = 0; b < 32; ++b) {
-      const int x = (wd << 5) + b;
-      if (x < W && occ[(size_t)x * H + y]) v |= (1u << b);
-    }
-    bits_x[(size_t)y * wpx + wd] = v;
+    bits[(size_t)tx * tiles_y + ty] = v;
   }
 }
 
 int apply_patch_batch(rl_method* m, const uint8_t* d_patches, const int* d_rects, const long long* d_offsets, int n) {
   if (n <= 0) return RL_OK;
-  patch_batch_kernel<<<n, 256, 0, m->stream>>>(m->d_occ, m->d_bits_y, m->d_bits_x, d_patches, d_rects, d_offsets, m->W,
-                                               m->H, m->wpy, m->wpx);
+  patch_batch_kernel<<<n, 256, 0, m->stream>>>(m->d_occ, m->d_bits_t, d_patches, d_rects, d_offsets, m->W, m->H,
+                                               m->tiles8_y());
   count_launch();
   RL_CHECK_LAUNCH();
   return RL_OK;
@@ -101,23 +77,14 @@ int apply_patch_batch(rl_method* m, const uint8_t* d_patches, const int* d_rects
 
 int upload_occupancy(rl_method* m, const rl_map* map) {
   const size_t n = (size_t)m->W * m->H;
-  m->wpy = (m->H + 31) / 32;
+  const long long tiles = (long long)m->tiles8_x() * m->tiles8_y();
   RL_CUDA(cudaMalloc(&m->d_occ, n ? n : 1));
-  m->wpx = (m->W + 31) / 32;
-  RL_CUDA(cudaMalloc(&m->d_bits_y, sizeof(uint32_t) * (size_t)m->W * m->wpy + 4));
-  RL_CUDA(cudaMalloc(&m->d_bits_x, sizeof(uint32_t) * (size_t)m->H * m->wpx + 4));
+  RL_CUDA(cudaMalloc(&m->d_bits_t, sizeof(unsigned long long) * (size_t)(tiles > 0 ? tiles : 1)));
   if (n) RL_CUDA(cudaMemcpyAsync(m->d_occ, map->occ.data(), n, cudaMemcpyHostToDevice, m->stream));
-  const long long total = (long long)m->W * m->wpy;
-  if (total > 0) {
-    pack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_y, m->W, m->H, m->wpy,
-                                                                            0, m->W, 0, m->wpy);
-    count_launch();
-    RL_CHECK_LAUNCH();
-  }
-  const long long total_x = (long long)m->H * m->wpx;
-  if (total_x > 0) {
-    pack_bits_x_kernel<<<(unsigned)((total_x + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_x, m->W, m->H,
-                                                                               m->wpx, 0, m->H, 0, m->wpx);
+  if (tiles > 0) {
+    pack_tiles_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_t, m->W, m->H,
+                                                                            m->tiles8_y(), 0, m->tiles8_x(), 0,
+                                                                            m->tiles8_y());
     count_launch();
     RL_CHECK_LAUNCH();
   }
@@ -128,16 +95,10 @@ int apply_patch(rl_method* m, const uint8_t* d_patch, int x0, int y0, int w, int
   patch_kernel<<<(w * h + 255) / 256, 256, 0, m->stream>>>(m->d_occ, d_patch, m->H, x0, y0, w, h);
   count_launch();
   RL_CHECK_LAUNCH();
-  const int wb = y0 >> 5, we = ((y0 + h - 1) >> 5) + 1;
-  const long long total = (long long)w * (we - wb);
-  pack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_y, m->W, m->H, m->wpy,
-                                                                          x0, x0 + w, wb, we);
-  count_launch();
-  RL_CHECK_LAUNCH();
-  const int xb = x0 >> 5, xe = ((x0 + w - 1) >> 5) + 1;
-  const long long total_x = (long long)h * (xe - xb);
-  pack_bits_x_kernel<<<(unsigned)((total_x + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_x, m->W, m->H, m->wpx,
-                                                                             y0, y0 + h, xb, xe);
+  const int tx0 = x0 >> 3, tx1 = ((x0 + w - 1) >> 3) + 1, ty0 = y0 >> 3, ty1 = ((y0 + h - 1) >> 3) + 1;
+  const long long tiles = (long long)(tx1 - tx0) * (ty1 - ty0);
+  pack_tiles_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_t, m->W, m->H,
+                                                                          m->tiles8_y(), tx0, tx1, ty0, ty1);
   count_launch();
   RL_CHECK_LAUNCH();
   return RL_OK;

@@ -465,3 +465,27 @@ def test_empty_map_and_empty_batches():
     w = np.zeros(0, np.float64)
     meth.calc_range_repeat_angles_eval_sensor_model(np.zeros((0, 3), np.float32), np.zeros(4, np.float32),
                                                     np.zeros(4, np.float32), w)
+
+
+def test_bl_persistent_kernel_matches_one_ray_per_thread():
+    """BL batches large enough for the persistent-warp kernel (lane re-queuing), all three entry points."""
+    occ = wl.load_map("basement_hallways_5cm")
+    W, H = occ.shape
+    world = (0.05, 0.0, -30.0, -30.0, 0.0, 1.0)
+    meth = make("bl", occ, world=world)
+    o = port.Oracle(port.BL, occ, MR, threads=8)
+    o.set_world(*world)
+    n = 500_009
+    q = wl.random_queries(W, H, n, seed=43)
+    out = np.empty(n, np.float32)
+    meth.calc_range_many_grid(q, out)
+    assert_bit_equal(out, o.calc_range_many(q), "grid")
+    parts = wl.grid_to_world(wl.random_queries(W, H, 7001, seed=44), world[0], world[2], world[3])
+    angles = wl.lidar_angles(71)
+    out = np.empty(len(parts) * len(angles), np.float32)
+    meth.calc_range_repeat_angles(parts, angles, out)
+    assert_bit_equal(out, o.numpy_calc_range_angles(parts, angles), "angles")
+    meth.set_persistent(0)
+    out2 = np.empty_like(out)
+    meth.calc_range_repeat_angles(parts, angles, out2)
+    assert_bit_equal(out2, out, "persistent vs one-ray-per-thread")
