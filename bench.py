@@ -235,11 +235,16 @@ def main():
         # "peer" (fused peer stores + symmetric-memory barrier) measured 31.1 us/step at N=2 against 34.7 us for
         # "signal" (one kernel per step with in-kernel epoch flags: every CTA pays a system-scope fence) when the
         # steps are replayed from a CUDA graph; launched eagerly "signal" is the faster one (33.7 vs 36.0 us).
-        want = os.environ.get("RL_BENCH_GATHER", "peer")
-        if want in ("peer", "signal"):
+        want = os.environ.get("RL_BENCH_GATHER", "pipelined")
+        if want in ("peer", "signal", "pipelined"):
             try:
                 from range_libc_b200 import parallel
-                if want == "signal":
+                if want == "pipelined":
+                    peer = parallel.PipelinedPeerStoreUpdate(world * N_PART, rm, angles, obs, device=dev)
+                    gather_mode = ("fused kernel epilogue: peer stores over NVLink into double-buffered symmetric memory; the "
+                                   "symmetric-memory barrier closing step k runs on a side stream and overlaps the compute "
+                                   "of step k+1")
+                elif want == "signal":
                     peer = parallel.SignalledSensorUpdate(world * N_PART, rm, angles, obs, device=dev)
                     gather_mode = ("one kernel per step: fused compute + peer stores over NVLink (symmetric memory, double "
                                    "buffered) + in-kernel epoch flags; no barrier launch, no NCCL call")
@@ -252,6 +257,7 @@ def main():
                 peer = None
                 gather_mode = "nccl all_gather_into_tensor (symmetric memory unavailable: %s)" % str(ex).splitlines()[0][:100]
     signalled = peer is not None and hasattr(peer, "flags")
+    pipelined = peer is not None and hasattr(peer, "finish")
 
     def step(i):
         if peer is not None:
@@ -268,6 +274,8 @@ def main():
         """close the last step: every rank's slice of the last gather has arrived (signalled mode)"""
         if signalled:
             rm.peers_wait()
+        if pipelined:
+            peer.finish()
 
     def barrier():
         if world > 1:
@@ -287,6 +295,8 @@ def main():
     try:
         if world > 1 and peer is None:
             raise RuntimeError("NCCL collectives are launched eagerly (no graph capture)")
+        if pipelined:
+            peer.reset()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(stream)
         graph = torch.cuda.CUDAGraph()
@@ -296,6 +306,8 @@ def main():
                 step(W_ + i)
             finish()
         rm.set_stream(stream.cuda_stream)
+        if pipelined:
+            peer.reset()
         graph.replay()  # untimed: instantiation / first-run costs
         barrier()
         mode = "cuda_graph"
@@ -303,6 +315,8 @@ def main():
         graph = None
         rm.set_stream(stream.cuda_stream)
         torch.cuda.synchronize()
+        if pipelined:
+            peer.reset()
         mode = "eager (graph capture failed: %s)" % str(ex).splitlines()[0][:120]
 
     l0 = rl.kernel_launches()

@@ -129,3 +129,67 @@ class SignalledSensorUpdate:
         if wait:
             self.method.peers_wait()
         return self.bufs[b]
+
+
+class PipelinedPeerStoreUpdate:
+    """PeerStoreSensorUpdate with the barrier of step k overlapped with the compute of step k+1: the gathered
+    weights are double buffered in symmetric memory, the fused kernel of step k stores into buffer k & 1 on the
+    main stream, and the symmetric-memory barrier that closes step k runs on a side stream while the kernel of
+    step k+1 is already computing.  Buffer k & 1 is reused by step k+2 only after its barrier has completed.
+    update() returns (buffer, event): the buffer holds the complete gather once the event has fired.
+    Throughput-oriented: the latency of one step is unchanged (kernel + barrier).  GPU only."""
+
+    def __init__(self, n_total, method, angles, obs, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.torch = torch
+        self.group = group or dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n_total = n_total
+        self.lo, self.hi = particle_slice(n_total, self.rank, self.world)
+        self.method, self.angles, self.obs = method, angles, obs
+        self.bufs, self.handles, self.ptrs = [], [], []
+        for _ in range(2):
+            t = symm_mem.empty(n_total, dtype=torch.float64, device=device)
+            h = symm_mem.rendezvous(t, self.group)
+            self.bufs.append(t)
+            self.handles.append(h)
+            self.ptrs.append([int(p) for p in h.buffer_ptrs])
+        self.side = torch.cuda.Stream(device=device)
+        self.done = [None, None]  # event: barrier of the last step that used buffer b has completed
+        self.k = 0
+
+    def update(self, local_particles):
+        torch = self.torch
+        main = torch.cuda.current_stream()
+        b = self.k & 1
+        if self.done[b] is not None:
+            main.wait_event(self.done[b])
+        self.method.calc_range_repeat_angles_eval_sensor_model_peers(local_particles, self.angles, self.obs,
+                                                                     self.ptrs[b], self.lo)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            self.handles[b].barrier()
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[b] = ev
+        self.k += 1
+        return self.bufs[b], ev
+
+    def reset(self):
+        """forget the events of earlier steps.  Call only when all earlier work has completed on every rank (e.g.
+        after a device synchronise + process-group barrier), and around CUDA-graph capture: a capturing stream
+        must not wait on events recorded outside the capture, nor eager work on events recorded inside it."""
+        self.done = [None, None]
+        self.k = 0
+
+    def finish(self):
+        """join the side stream: every gather issued so far is complete once the main stream gets here"""
+        main = self.torch.cuda.current_stream()
+        for ev in self.done:
+            if ev is not None:
+                main.wait_event(ev)

@@ -68,8 +68,27 @@ def main():
         results["signalled"] = ok_all
     except Exception as ex:  # noqa: BLE001
         results["signalled"] = "unavailable: %s" % str(ex).splitlines()[0]
+    try:
+        pipe = parallel.PipelinedPeerStoreUpdate(n_total, rm, angles, obs, device=dev)
+        ok_all = True
+        outs = []
+        for it in range(5):
+            shift = torch.tensor([0.25 * it, -0.5 * it, 0.01 * it], device=dev)
+            buf, ev = pipe.update(mine + shift)
+            if it in (3, 4):  # the last use of each buffer
+                outs.append((it, buf, ev))
+        pipe.finish()
+        torch.cuda.synchronize()
+        for it, buf, ev in outs:
+            shift = torch.tensor([0.25 * it, -0.5 * it, 0.01 * it], device=dev)
+            ref_it = ora.calc_range_repeat_angles_eval_sensor_model(
+                (torch.from_numpy(particles).to(dev) + shift).cpu().numpy(), angles_h, obs_h)
+            ok_all &= bool(np.array_equal(buf.cpu().numpy().view(np.uint64), ref_it.view(np.uint64)))
+        results["pipelined"] = ok_all
+    except Exception as ex:  # noqa: BLE001
+        results["pipelined"] = "unavailable: %s" % str(ex).splitlines()[0]
     print("rank %d/%d: %s" % (rank, world, results), flush=True)
-    ok = results["nccl"] is True and all(results[k] is True or isinstance(results[k], str) for k in ("peer", "signalled"))
+    ok = results["nccl"] is True and all(results[k] is True or isinstance(results[k], str) for k in ("peer", "signalled", "pipelined"))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
