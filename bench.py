@@ -155,6 +155,46 @@ def cpu_reference_run(occ, sets, angles, obs, table, steps, warmup, threads, bud
     return done * N_PART * N_BEAMS / dt, kind, done, dt
 
 
+def reference_cuda_run(occ, sets, angles, obs, table, budget_s=5.0):
+    """The reference's own CUDA path (RayMarchingGPU + includes/kernels.cu recompiled for sm_100a, oracle/_ref/
+    libref_cuda.so) on the same step, the way the reference documents it for a particle filter: ranges on the GPU
+    through numpy_calc_range_angles with host buffers (its only interface: cudaMemcpy in, kernel, cudaMemcpy out,
+    device sync), then RangeMethod::eval_sensor_model on one host thread (its fused GPU variant prints
+    "unimplemented", kernels.cu:281-284).  Returns None when the library is absent."""
+    from oracle import ref
+    if not ref.available("cuda"):
+        return None
+    rmap = ref.RefMap(occ=occ, flavor="cuda")
+    meth = ref.RefMethod(ref.RMGPU, rmap, MAX_RANGE)
+    meth.set_sensor_model(table)
+    n_rays = N_PART * N_BEAMS
+
+    def timed(fn):
+        for i in range(3):
+            fn(i)
+        t0, done = time.perf_counter(), 0
+        while time.perf_counter() - t0 < budget_s / 2 and done < 5000:
+            fn(done)
+            done += 1
+        return (time.perf_counter() - t0) / done, done
+
+    ranges = [None]
+
+    def cast(i):
+        ranges[0] = meth.numpy_calc_range_angles(sets[i % len(sets)], angles)
+
+    def step(i):
+        cast(i)
+        meth.eval_sensor_model(obs, ranges[0], N_BEAMS, N_PART)
+
+    t_cast, n1 = timed(cast)
+    t_step, n2 = timed(step)
+    return {"ranges_only_rays_per_s": n_rays / t_cast, "ranges_only_ms": t_cast * 1e3,
+            "value": n_rays / t_step, "ms_per_step": t_step * 1e3, "unit": "rays/s", "steps": n2,
+            "what": "reference RayMarchingGPU.numpy_calc_range_angles (kernels.cu recompiled for sm_100a, CHUNK_SIZE 262144, "
+                    "NUM_THREADS 256, host buffers) + RangeMethod::eval_sensor_model on 1 host thread; compare with e2e"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -464,6 +504,10 @@ def main():
                                     done, dt, threads)}
         v1, kind1, done1, dt1 = cpu_reference_run(occ, sets_h, angles_h, obs_h, table, 100000, 1, 1, budget_s=5.0)
         line["cpu_baseline"]["single_thread_value"] = v1
+        try:
+            line["reference_cuda_baseline"] = reference_cuda_run(occ, sets_h, angles_h, obs_h, table)
+        except Exception as ex:  # noqa: BLE001
+            line["reference_cuda_baseline"] = {"unavailable": str(ex).splitlines()[0][:120]}
         if not args.no_extra:
             line["extra"] = extra_throughput(rl, wl, occ, omap, dev, stream, peak)
     print(json.dumps(line), flush=True)

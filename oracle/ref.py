@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 BL, RM, CDDT, PCDDT, GLT = 0, 1, 2, 3, 4
+RMGPU = 5  # ranges::RayMarchingGPU; only in flavor "cuda" (libref_cuda.so: the reference's kernels.cu for sm_100a)
 
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)

@@ -8,6 +8,11 @@
 // Used by: tests/ (to pin oracle/rangelib_oracle.c and to generate tests/golden/*),
 // bench.py's cpu_baseline leg and `bench.py --impl reference` (kind = "reference").
 //
+// With -DUSE_CUDA=1 (oracle/_ref/libref_cuda.so, linked with the reference's own includes/kernels.cu
+// compiled for sm_100a) kind 5 is ranges::RayMarchingGPU, the reference's CUDA path: the baseline "recompiled
+// reference kernels" figure in bench.py.  Its batched methods are non-virtual and shadow the base class's
+// (RangeLib.h:819-911), so they are called through the concrete pointer.
+//
 // Threading: the reference is single-threaded.  The *_mt entry points split the batch
 // into contiguous slices and run the reference's own batched loop on each slice from a
 // std::thread; calc_range is read-only with the reference's default flags
@@ -41,6 +46,9 @@ struct RefMethod {
   RMOpen* rm = nullptr;
   ranges::CDDTCast* cddt = nullptr;
   GLTOpen* glt = nullptr;
+#if USE_CUDA == 1
+  ranges::RayMarchingGPU* gpu = nullptr;
+#endif
 };
 
 template <class F>
@@ -62,6 +70,8 @@ void run_sliced(int n, int nthreads, F f) {
 }  // namespace
 
 extern "C" {
+
+int ref_has_cuda() { return USE_CUDA == 1; }
 
 // occ is x-major: occ[x*H + y] != 0 <=> OMap::grid[x][y] (RangeLib.h:126).
 void* ref_map_create(const uint8_t* occ, int W, int H) {
@@ -139,6 +149,11 @@ void* ref_method_create(int kind, void* mp, float max_range, unsigned td) {
   } else if (kind == 4) {
     r->glt = new GLTOpen(*m, max_range, (int)td);
     r->base = r->glt;
+#if USE_CUDA == 1
+  } else if (kind == 5) {
+    r->gpu = new ranges::RayMarchingGPU(*m, max_range);
+    r->base = r->gpu;
+#endif
   } else {
     delete r;
     return nullptr;
@@ -176,6 +191,9 @@ float ref_calc_range(void* rp, float x, float y, float heading) {
 // grid coordinates, no conversion: what RayMarchingGPU::calc_range_many computes
 // (RangeLib.h:819-831) and what main.cpp's benchmarks call per ray.
 void ref_calc_range_many(void* rp, const float* ins, float* outs, int n, int nthreads) {
+#if USE_CUDA == 1
+  if (((RefMethod*)rp)->gpu) return ((RefMethod*)rp)->gpu->calc_range_many(const_cast<float*>(ins), outs, n);
+#endif
   ranges::RangeMethod* b = ((RefMethod*)rp)->base;
   run_sliced(n, nthreads, [=](int lo, int hi) {
     for (int i = lo; i < hi; ++i) outs[i] = b->calc_range(ins[3 * i], ins[3 * i + 1], ins[3 * i + 2]);
@@ -183,6 +201,9 @@ void ref_calc_range_many(void* rp, const float* ins, float* outs, int n, int nth
 }
 
 void ref_numpy_calc_range(void* rp, const float* ins, float* outs, int n, int nthreads) {
+#if USE_CUDA == 1
+  if (((RefMethod*)rp)->gpu) return ((RefMethod*)rp)->gpu->numpy_calc_range(const_cast<float*>(ins), outs, n);
+#endif
   ranges::RangeMethod* b = ((RefMethod*)rp)->base;
   run_sliced(n, nthreads, [=](int lo, int hi) {
     b->numpy_calc_range(const_cast<float*>(ins) + 3 * (size_t)lo, outs + lo, hi - lo);
@@ -191,6 +212,10 @@ void ref_numpy_calc_range(void* rp, const float* ins, float* outs, int n, int nt
 
 void ref_numpy_calc_range_angles(void* rp, const float* ins, const float* angles, float* outs, int n, int m,
                                  int nthreads) {
+#if USE_CUDA == 1
+  if (((RefMethod*)rp)->gpu)
+    return ((RefMethod*)rp)->gpu->numpy_calc_range_angles(const_cast<float*>(ins), const_cast<float*>(angles), outs, n, m);
+#endif
   ranges::RangeMethod* b = ((RefMethod*)rp)->base;
   run_sliced(n, nthreads, [=](int lo, int hi) {
     b->numpy_calc_range_angles(const_cast<float*>(ins) + 3 * (size_t)lo, const_cast<float*>(angles),
@@ -199,6 +224,9 @@ void ref_numpy_calc_range_angles(void* rp, const float* ins, const float* angles
 }
 
 void ref_set_sensor_model(void* rp, const double* table, int k) {
+#if USE_CUDA == 1
+  if (((RefMethod*)rp)->gpu) return ((RefMethod*)rp)->gpu->set_sensor_model(const_cast<double*>(table), k);
+#endif
   ((RefMethod*)rp)->base->set_sensor_model(const_cast<double*>(table), k);
 }
 
