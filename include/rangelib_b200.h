@@ -92,6 +92,17 @@ int rl_method_update_map(rl_method* m, const uint8_t* patch_xmajor, int x0, int 
 /* the same for n non-overlapping patches in ONE launch: rects = n x (x0, y0, w, h) (HOST ints); the
  * patches' bytes are concatenated in `patches` (HOST or DEVICE), each x-major inside its rectangle. */
 int rl_method_update_map_batch(rl_method* m, const uint8_t* patches_xmajor, const int* rects, int n);
+/* Whole-map ingest on the device: replace the occupancy of an existing handle (same size) from a source image in
+ * HOST or DEVICE memory and refresh the kind's structures -- a mapping pipeline that keeps its grid in HBM never
+ * copies it to the host.
+ *  - occupancy_grid: ROS nav_msgs/OccupancyGrid `data` (int8 row-major [rows][cols]) with the reference's
+ *    PyOMap(OccupancyGrid) rule (RangeLibc.pyx:146-157): OMap(rows, cols), grid[x][y] = data[x*cols+y] > 10,
+ *    so rows must equal the map width and cols its height;
+ *  - rgba: RGBA8 rows as lodepng_decode32 yields them, with OMap(filename, threshold)'s conversion
+ *    (RangeLib.h:189-199, RangeUtils.h:30-32): gray from bytes (2,1,0), occupied iff (int)gray < threshold;
+ *    img_w / img_h must equal the map width / height. */
+int rl_method_set_map_occupancy_grid(rl_method* m, const int8_t* data, int rows, int cols);
+int rl_method_set_map_rgba(rl_method* m, const uint8_t* rgba, int img_w, int img_h, float threshold);
 /* bytes of device memory held by the acceleration structure (RangeMethod::memory()) */
 int64_t rl_method_memory(const rl_method* m);
 
@@ -121,6 +132,15 @@ int rl_eval_sensor_model(rl_method* m, const float* obs, const float* ranges, do
 int rl_calc_range_repeat_angles_eval_sensor_model(rl_method* m, const float* ins, const float* angles,
                                                   const float* obs, double* weights, int num_particles,
                                                   int num_angles);
+/* RangeMethod::calc_range_many_radial_optimized(ins,outs,num_particles,num_rays,min_angle,max_angle)
+ * RangeLib.h:616-676 (PyCDDTCast.calc_range_many_radial_optimized, RangeLibc.pyx:274-276): a lidar fan of
+ * num_rays beams from min_angle to max_angle per pose; beam a <= num_rays/3 and the beam pi further round come
+ * from one CDDTCast::calc_range_pair (:1521-1649), the beams between from calc_range.  outs is
+ * [num_particles][num_rays]; as in the reference, beams beyond the last paired one are NOT written (outs is
+ * read-modify-write for host pointers), and kinds without calc_range_pair store -world_scale in the paired
+ * slots (:419).  Second beams that fall outside the row are dropped (the reference writes past it). */
+int rl_calc_range_many_radial_optimized(rl_method* m, const float* ins, float* outs, int num_particles, int num_rays,
+                                        float min_angle, float max_angle);
 
 /* Multi-GPU form of the fused call (one process per GPU, particles sharded across ranks, map and
  * tables replicated): the kernel's epilogue stores this rank's `num_particles` weights directly into
@@ -152,6 +172,8 @@ int rl_calc_range_repeat_angles_eval_sensor_model_signalled(rl_method* m, const 
 int rl_method_peers_wait(rl_method* m);
 
 /* ---- table-level access for parity tests ---------------------------------------------------- */
+/* the occupancy bytes resident on the device, x-major out[x*H+y] (after dynamic updates / device ingest). out: HOST */
+int rl_debug_get_occ(rl_method* m, uint8_t* out);
 /* distance transform, x-major out[x*H+y] (DistanceTransform::grid RangeLib.h:328); RL_RM only. out: HOST */
 int rl_debug_get_dt(rl_method* m, float* out);
 /* CDDT tables (CDDTCast::compressed_lut / lut_translations RangeLib.h:1746-1748) in CSR form.

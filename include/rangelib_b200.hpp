@@ -67,6 +67,10 @@ class RangeMethod {
                                                   int num_particles, int num_angles) {
     check(rl_calc_range_repeat_angles_eval_sensor_model(h_, ins, angles, obs, weights, num_particles, num_angles));
   }
+  void calc_range_many_radial_optimized(float* ins, float* outs, int num_particles, int num_rays, float min_angle,
+                                        float max_angle) {
+    check(rl_calc_range_many_radial_optimized(h_, ins, outs, num_particles, num_rays, min_angle, max_angle));
+  }
   float maxRange() const { return max_range_; }
   long long memory() const { return (long long)rl_method_memory(h_); }
   rl_method* handle() { return h_; }

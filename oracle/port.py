@@ -68,6 +68,7 @@ def _load():
     L.orc_numpy_calc_range.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int]
     L.orc_numpy_calc_range_angles.argtypes = [C.c_void_p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
     L.orc_set_sensor_model.argtypes = [C.c_void_p, _f64p, C.c_int]
+    L.orc_calc_range_many_radial_optimized.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float]
     L.orc_eval_sensor_model.argtypes = [C.c_void_p, _f32p, _f32p, _f64p, C.c_int, C.c_int, C.c_int]
     L.orc_calc_range_repeat_angles_eval_sensor_model.argtypes = [
         C.c_void_p, _f32p, _f32p, _f32p, _f64p, C.c_int, C.c_int, C.c_int]
@@ -173,6 +174,14 @@ class Oracle:
             self.h, _p(ins, _f32p), _p(angles, _f32p), _p(obs, _f32p), _p(w, _f64p), ins.shape[0],
             angles.shape[0], self.threads)
         return w
+
+    def calc_range_many_radial_optimized(self, num_rays, min_angle, max_angle, ins, outs):
+        """RangeLib.h:616-676; outs f32[N*num_rays] updated in place."""
+        ins = _f32(ins)
+        assert outs.dtype == np.float32 and outs.flags.c_contiguous and outs.size >= ins.shape[0] * num_rays
+        self.L.orc_calc_range_many_radial_optimized(self.h, _p(ins, _f32p), _p(outs, _f32p), ins.shape[0], num_rays,
+                                                    min_angle, max_angle)
+        return outs
 
     def rm_step_counts(self, ins_grid):
         ins = _f32(ins_grid)

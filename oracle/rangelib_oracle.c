@@ -593,6 +593,62 @@ static float cddt_calc_range(const orc_ctx* c, float x, float y, float heading) 
   return -1.0f; /* the reference's assert(0) fall-through (:1514) */
 }
 
+/* CDDTCast::calc_range_pair, RangeLib.h:1521-1649: (range along heading, range along heading + pi).
+ * The reference does not bounds-check lut_index (:1538-1539; undefined outside the table) -- here
+ * (max_range, max_range).  Its non-flipped occupied-cell test is a no-op (:1612) and is omitted. */
+static void cddt_calc_range_pair(const orc_ctx* c, float x, float y, float heading, float* r, float* r_inv) {
+  int a, flipped;
+  float dth;
+  cddt_discretize_theta(c->td, (float)(-1.0 * (double)heading), &a, &dth, &flipped);
+  float ca = cosf(dth), sa = sinf(dth);
+  float lx = x * ca - y * sa;
+  float ly = (x * sa + y * ca) + c->trans[a];
+  unsigned li = (unsigned)(int)ly;
+  float mr = c->max_range;
+  *r = mr;
+  *r_inv = mr;
+  if (li >= (unsigned)c->widths[a]) return;
+  int64_t b = c->slice0[a] + li;
+  const float* B = c->values + c->offsets[b];
+  int size = (int)(c->offsets[b + 1] - c->offsets[b]);
+  int high = size - 1;
+  if (high == -1) return;
+  int index = 0;
+  if (flipped) {
+    if (B[0] > lx) { *r_inv = fminf(mr, B[0] - lx); return; }  /* std::min(max_range, .) :1553 */
+    if (B[high] < lx) { *r = lx - B[high]; return; }
+    if (occ_at(c, (int)x, (int)y)) { *r = 0.0f; *r_inv = 0.0f; return; }
+    if (high > ORC_BINARY_SEARCH_THRESHOLD) { /* upper_bound - 1 :1566 */
+      int lo = 0, hi = size;
+      while (lo < hi) {
+        int mid = lo + (hi - lo) / 2;
+        if (!(lx < B[mid])) lo = mid + 1; else hi = mid;
+      }
+      index = lo - 1;
+    } else {
+      for (int i = high; i >= 0; --i)
+        if (B[i] <= lx) { index = i; break; }
+    }
+    *r = lx - B[index];
+    if (index + 1 != size) *r_inv = B[index + 1] - lx;
+  } else {
+    if (B[high] < lx) { *r_inv = fminf(mr, lx - B[high]); return; }
+    if (high > ORC_BINARY_SEARCH_THRESHOLD) { /* lower_bound :1619 */
+      int lo = 0, hi = size;
+      while (lo < hi) {
+        int mid = lo + (hi - lo) / 2;
+        if (B[mid] < lx) lo = mid + 1; else hi = mid;
+      }
+      index = lo;
+    } else {
+      for (int i = 0; i < size; ++i)
+        if (B[i] >= lx) { index = i; break; }
+    }
+    *r = B[index] - lx;
+    if (index - 1 != -1) *r_inv = lx - B[index - 1];
+  }
+}
+
 /* ------------------------------------------------------------------------------------------
  * GiantLUTCast, RangeLib.h:1772-1904 (_GIANT_LUT_SHORT_DATATYPE 1, _USE_CACHED_CONSTANTS 1,
  * _USE_ALTERNATE_MOD 1, _USE_FAST_ROUND 0): a uint16 range for every (x, y, theta bin), seeded by
@@ -829,4 +885,40 @@ void orc_calc_range_repeat_angles_eval_sensor_model(const orc_ctx* c, const floa
                                                     int nthreads) {
   job_t j = {c, 4, ins, angles, obs, NULL, NULL, weights, 0, 0, m};
   run_jobs(j, n, nthreads);
+}
+
+/* RangeMethod::calc_range_many_radial_optimized, RangeLib.h:616-676.  Sequential like the reference, so that a
+ * pair's second beam overwritten by a later iteration ends with the later value; writes that would leave the
+ * particle's row (the reference lets them run into the next row or past the buffer) are dropped. */
+void orc_calc_range_many_radial_optimized(const orc_ctx* c, const float* ins, float* outs, int n, int num_rays,
+                                          float min_angle, float max_angle) {
+  xform_t t = make_xform(c);
+  float step = (max_angle - min_angle) / (num_rays - 1);
+  int max_pairwise_index = (float)num_rays / 3.0;
+  float index_offset_float = (num_rays - 1.0) * M_PI / (max_angle - min_angle);
+  int index_offset = roundf(index_offset_float);
+  int is_cddt = c->kind == 2; /* CDDT, pruned or not */
+  for (int i = 0; i < n; ++i) {
+    float xw = ins[3 * i], yw = ins[3 * i + 1], thw = ins[3 * i + 2];
+    float theta = -thw + t.rot;
+    float x = (xw - t.ox) * t.inv;
+    float y = (yw - t.oy) * t.inv;
+    float tmp = x;
+    x = t.co * x - t.s * y;
+    y = t.s * tmp + t.co * y;
+    float angle = min_angle;
+    float* row = outs + (size_t)i * num_rays;
+    int a;
+    for (a = 0; a <= max_pairwise_index; ++a) {
+      float r = -1.0f, r_inv = -1.0f; /* RangeMethod::calc_range_pair default :419 */
+      if (is_cddt) cddt_calc_range_pair(c, y, x, theta - angle, &r, &r_inv);
+      if (a < num_rays) row[a] = r * t.scale;
+      if (a + index_offset >= 0 && a + index_offset < num_rays) row[a + index_offset] = r_inv * t.scale;
+      angle += step;
+    }
+    for (a = max_pairwise_index + 1; a < index_offset; ++a) {
+      if (a < num_rays) row[a] = calc_range_any(c, y, x, theta - angle) * t.scale;
+      angle += step;
+    }
+  }
 }

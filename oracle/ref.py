@@ -58,6 +58,8 @@ def _load(flavor):
     L.ref_eval_sensor_model.argtypes = [C.c_void_p, _f32p, _f32p, _f64p, C.c_int, C.c_int, C.c_int]
     L.ref_calc_range_repeat_angles_eval_sensor_model.argtypes = [
         C.c_void_p, _f32p, _f32p, _f32p, _f64p, C.c_int, C.c_int, C.c_int]
+    L.ref_calc_range_many_radial_optimized.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float]
+    L.ref_calc_range_pair.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, _f32p, _f32p]
     L.ref_get_dt.argtypes = [C.c_void_p, _f32p]
     L.ref_cddt_dims.restype = C.c_int64
     L.ref_cddt_dims.argtypes = [C.c_void_p, _i64p, _i32p, _f32p]
@@ -164,6 +166,19 @@ class RefMethod:
             self.h, _p(ins, _f32p), _p(angles, _f32p), _p(obs, _f32p), _p(w, _f64p), ins.shape[0],
             angles.shape[0], self.threads)
         return w
+
+    def calc_range_many_radial_optimized(self, num_rays, min_angle, max_angle, ins, outs):
+        """outs f32[N*num_rays] is updated in place (the reference leaves some beams unwritten)."""
+        ins = _f32(ins)
+        assert outs.dtype == np.float32 and outs.flags.c_contiguous and outs.size >= ins.shape[0] * num_rays
+        self.L.ref_calc_range_many_radial_optimized(self.h, _p(ins, _f32p), _p(outs, _f32p), ins.shape[0], num_rays,
+                                                    min_angle, max_angle)
+        return outs
+
+    def calc_range_pair(self, x, y, th):
+        r, ri = C.c_float(), C.c_float()
+        self.L.ref_calc_range_pair(self.h, x, y, th, C.byref(r), C.byref(ri))
+        return r.value, ri.value
 
     def dt(self):
         out = np.empty((self.map.width, self.map.height), np.float32)

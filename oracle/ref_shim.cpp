@@ -250,6 +250,19 @@ void ref_calc_range_repeat_angles_eval_sensor_model(void* rp, const float* ins, 
   });
 }
 
+// RangeMethod::calc_range_many_radial_optimized (RangeLib.h:616-676), single-threaded as shipped
+void ref_calc_range_many_radial_optimized(void* rp, const float* ins, float* outs, int n, int num_rays,
+                                          float min_angle, float max_angle) {
+  ((RefMethod*)rp)->base->calc_range_many_radial_optimized(const_cast<float*>(ins), outs, n, num_rays, min_angle,
+                                                           max_angle);
+}
+
+void ref_calc_range_pair(void* rp, float x, float y, float heading, float* r, float* r_inv) {
+  std::pair<float, float> p = ((RefMethod*)rp)->base->calc_range_pair(x, y, heading);
+  *r = p.first;
+  *r_inv = p.second;
+}
+
 // distance transform dump, x-major out[x*H+y]; RM only.
 int ref_get_dt(void* rp, float* out) {
   RefMethod* r = (RefMethod*)rp;

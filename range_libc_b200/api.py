@@ -20,7 +20,7 @@ def _buf(a, dtype, ndim, name):
     typed-memoryview checks of the reference's Cython signatures (ValueError on mismatch)."""
     if _is_torch(a):
         import torch
-        want = {np.float32: torch.float32, np.float64: torch.float64, np.uint8: torch.uint8}[dtype]
+        want = {np.float32: torch.float32, np.float64: torch.float64, np.uint8: torch.uint8, np.int8: torch.int8}[dtype]
         if a.dtype != want:
             raise ValueError("%s: expected dtype %s, got %s" % (name, want, a.dtype))
         if a.dim() != ndim:
@@ -158,6 +158,16 @@ class _RangeMethod:
             raise ValueError("shape mismatch")
         check(lib().rl_calc_range_repeat_angles_eval_sensor_model(self._h, pi, pa, pb, pw, si[0], sa[0]))
 
+    def calc_range_many_radial_optimized(self, num_rays, min_angle, max_angle, ins, outs):
+        """RangeLibc.pyx:274-276 (argument order as there).  outs f32[N*num_rays], updated in place: beams the
+        reference does not write keep their previous content."""
+        pi, si = _buf(ins, np.float32, 2, "ins")
+        po, so = _buf(outs, np.float32, 1, "outs")
+        if si[1] != 3 or so[0] < si[0] * int(num_rays):
+            raise ValueError("shape mismatch")
+        check(lib().rl_calc_range_many_radial_optimized(self._h, pi, po, si[0], int(num_rays), float(min_angle),
+                                                        float(max_angle)))
+
     def calc_range_repeat_angles_eval_sensor_model_peers(self, ins, angles, obs, peer_ptrs, offset):
         """Multi-GPU fused update: weights of the local particles `ins` are stored by the kernel into every
         rank's gathered array (peer_ptrs: one peer-mapped device pointer per rank) at `offset`."""
@@ -230,6 +240,24 @@ class _RangeMethod:
             pp, sp = _buf(patch_xmajor, np.uint8, 2, "patch")
         check(lib().rl_method_update_map(self._h, pp, int(x0), int(y0), sp[0], sp[1]))
 
+    def set_map_occupancy_grid(self, data):
+        """Replace the whole map on the device from ROS OccupancyGrid data: int8 [rows, cols] (numpy or torch CUDA
+        tensor), occupied iff value > 10, rows = map width (RangeLibc.pyx:146-157)."""
+        if not _is_torch(data):
+            data = np.ascontiguousarray(data, dtype=np.int8)
+        pd, sd = _buf(data, np.int8, 2, "data")
+        check(lib().rl_method_set_map_occupancy_grid(self._h, pd, sd[0], sd[1]))
+
+    def set_map_rgba(self, rgba, threshold=128.0):
+        """Replace the whole map on the device from an RGBA8 image [rows, cols, 4] (numpy or torch CUDA tensor) with
+        the reference's OMap(png, threshold) conversion (RangeLib.h:189-199); cols = map width, rows = map height."""
+        if not _is_torch(rgba):
+            rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+        pr, sr = _buf(rgba, np.uint8, 3, "rgba")
+        if sr[2] != 4:
+            raise ValueError("rgba must be [rows, cols, 4]")
+        check(lib().rl_method_set_map_rgba(self._h, pr, sr[1], sr[0], float(threshold)))
+
     def update_map_batch(self, patches, rects):
         """Dynamic maps: n non-overlapping patches in one launch.  rects: int32 [n, 4] (x0, y0, w, h) host array;
         patches: uint8 1-D, the patches' bytes concatenated (numpy or torch CUDA tensor)."""
@@ -240,6 +268,12 @@ class _RangeMethod:
         if rects.ndim != 2 or rects.shape[1] != 4 or int((rects[:, 2].astype(np.int64) * rects[:, 3]).sum()) != sp[0]:
             raise ValueError("rects must be [n,4] and patches must hold sum(w*h) bytes")
         check(lib().rl_method_update_map_batch(self._h, pp, C.c_void_p(rects.ctypes.data), rects.shape[0]))
+
+    def occupancy(self):
+        """The occupancy resident on the device, uint8 [W, H] x-major."""
+        out = np.empty((self._map.width(), self._map.height()), np.uint8)
+        check(lib().rl_debug_get_occ(self._h, C.c_void_p(out.ctypes.data)))
+        return out
 
     def memory(self):
         return int(lib().rl_method_memory(self._h))

@@ -42,6 +42,10 @@ SIGNATURES = {
     "rl_set_sensor_model": (_i, [_vp, _vp, _i]),
     "rl_eval_sensor_model": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
     "rl_calc_range_repeat_angles_eval_sensor_model": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "rl_method_set_map_occupancy_grid": (_i, [_vp, _vp, _i, _i]),
+    "rl_method_set_map_rgba": (_i, [_vp, _vp, _i, _i, C.c_float]),
+    "rl_debug_get_occ": (_i, [_vp, _vp]),
+    "rl_calc_range_many_radial_optimized": (_i, [_vp, _vp, _vp, _i, _i, C.c_float, C.c_float]),
     "rl_calc_range_repeat_angles_eval_sensor_model_peers": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_vp), _i, C.c_int64, _i, _i]),
     "rl_method_peers_init": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i]),
     "rl_calc_range_repeat_angles_eval_sensor_model_signalled": (_i, [_vp, _vp, _vp, _vp, C.c_int64, _i, _i, C.POINTER(_i)]),

@@ -2,7 +2,9 @@
 // Handles, pointer classification (host vs device), staging for host-pointer calls, dispatch.
 // There is no CPU fallback anywhere in this library: without a usable device every entry point
 // that computes fails with RL_E_NO_DEVICE.
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -98,7 +100,12 @@ class Marshal {
   static constexpr int kMax = 6;
   explicit Marshal(rl_method* m) : m_(m) {}
   int add(const void* p, size_t bytes, bool output) {
-    a_[n_] = Arg{const_cast<void*>(p), bytes, output, nullptr, 0, SIDE_PAGEABLE};
+    a_[n_] = Arg{const_cast<void*>(p), bytes, output, nullptr, 0, SIDE_PAGEABLE, false};
+    return n_++;
+  }
+  // a buffer the kernel updates in part: travels to the device with the inputs and comes back whole
+  int add_inout(void* p, size_t bytes) {
+    a_[n_] = Arg{p, bytes, false, nullptr, 0, SIDE_PAGEABLE, true};
     return n_++;
   }
   void* dev(int i) const { return a_[i].dev; }
@@ -167,16 +174,22 @@ class Marshal {
       if (!zc_out_ && out_bytes_)
         RL_CUDA(cudaMemcpyAsync((char*)m_->h_stage + in_bytes_, (char*)m_->d_stage + in_bytes_, out_bytes_,
                                 cudaMemcpyDeviceToHost, m_->stream));
+      for (int i = 0; i < n_; ++i) {
+        Arg& a = a_[i];
+        if (a.host && a.bytes && a.inout)
+          RL_CUDA(cudaMemcpyAsync((char*)m_->h_stage + a.off, (char*)m_->d_stage + a.off, a.bytes,
+                                  cudaMemcpyDeviceToHost, m_->stream));
+      }
       RL_CUDA(cudaStreamSynchronize(m_->stream));
       for (int i = 0; i < n_; ++i) {
         Arg& a = a_[i];
-        if (a.host && a.bytes && a.output) memcpy(a.host, (char*)m_->h_stage + a.off, a.bytes);
+        if (a.host && a.bytes && (a.output || a.inout)) memcpy(a.host, (char*)m_->h_stage + a.off, a.bytes);
       }
       return RL_OK;
     }
     for (int i = 0; i < n_; ++i) {
       Arg& a = a_[i];
-      if (a.host && a.bytes && a.output)
+      if (a.host && a.bytes && (a.output || a.inout))
         RL_CUDA(cudaMemcpyAsync(a.host, a.dev, a.bytes, cudaMemcpyDeviceToHost, m_->stream));
     }
     RL_CUDA(cudaStreamSynchronize(m_->stream));
@@ -191,6 +204,7 @@ class Marshal {
     void* dev;
     size_t off;
     Side side;
+    bool inout;
   };
   rl_method* m_;
   Arg a_[kMax];
@@ -230,6 +244,34 @@ static int run_cast(rl_method* m, int mode, const float* ins, const float* angle
   return ms.finish();
 }
 
+// after the occupancy changed on the device: rebuild what the kind derives from it
+static int refresh_structures(rl_method* m) {
+  int rc = RL_OK;
+  if (m->kind == RL_RM || m->kind == RL_GLT) rc = build_distance_transform(m);
+  if (!rc && m->kind == RL_GLT) rc = glt_build(m);
+  if (m->kind == RL_CDDT || m->kind == RL_PCDDT) {
+    const bool was_pruned = m->pruned;
+    rc = cddt_build(m);
+    if (!rc && was_pruned) rc = cddt_prune(m, m->max_range);
+  }
+  return rc;
+}
+
+// whole-map replacement from a device- or host-resident source image; `bytes` of it are staged when on the host
+template <class F>
+static int replace_map(rl_method* m, const void* src, size_t bytes, F ingest) {
+  const void* d_src = src;
+  if (bytes && !is_device_ptr(src)) {
+    int rc = ensure_stage(m, bytes);
+    if (rc) return rc;
+    RL_CUDA(cudaMemcpyAsync(m->d_stage, src, bytes, cudaMemcpyHostToDevice, m->stream));
+    d_src = m->d_stage;
+  }
+  int rc = ingest(d_src);
+  if (rc) return rc;
+  return refresh_structures(m);
+}
+
 static void free_method(rl_method* m) {
   if (!m) return;
   cudaSetDevice(m->device);
@@ -242,6 +284,7 @@ static void free_method(rl_method* m) {
   cudaFree(m->d_stage);
   cudaFree(m->d_epoch);
   cudaFree(m->d_counter);
+  cudaFree(m->d_radial);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
@@ -422,14 +465,27 @@ int rl_method_update_map(rl_method* m, const uint8_t* patch, int x0, int y0, int
   }
   rc = apply_patch(m, d_patch, x0, y0, w, h);
   if (rc) return rc;
-  if (m->kind == RL_RM || m->kind == RL_GLT) rc = build_distance_transform(m);
-  if (!rc && m->kind == RL_GLT) rc = glt_build(m);
-  if (m->kind == RL_CDDT || m->kind == RL_PCDDT) {
-    const bool was_pruned = m->pruned;
-    rc = cddt_build(m);
-    if (!rc && was_pruned) rc = cddt_prune(m, m->max_range);
+  return refresh_structures(m);
+}
+
+int rl_method_set_map_occupancy_grid(rl_method* m, const int8_t* data, int rows, int cols) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (rows != m->W || cols != m->H || (!data && (size_t)rows * cols > 0)) {
+    set_error("rl_method_set_map_occupancy_grid: need data[rows][cols] with rows == map width and cols == map height");
+    return RL_E_INVALID;
   }
-  return rc;
+  return replace_map(m, data, (size_t)rows * cols, [&](const void* d) { return ingest_occupancy_grid(m, (const int8_t*)d); });
+}
+
+int rl_method_set_map_rgba(rl_method* m, const uint8_t* rgba, int img_w, int img_h, float threshold) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (img_w != m->W || img_h != m->H || (!rgba && (size_t)img_w * img_h > 0)) {
+    set_error("rl_method_set_map_rgba: image size differs from the map's");
+    return RL_E_INVALID;
+  }
+  return replace_map(m, rgba, (size_t)img_w * img_h * 4, [&](const void* d) { return ingest_rgba(m, (const uint8_t*)d, threshold); });
 }
 
 int rl_debug_set_coop_threshold(rl_method* m, int lanes) {
@@ -479,14 +535,7 @@ int rl_method_update_map_batch(rl_method* m, const uint8_t* patches, const int* 
   rc = apply_patch_batch(m, d_patches, (const int*)base, (const long long*)(base + b_rects), n);
   if (rc) return rc;
   RL_CUDA(cudaStreamSynchronize(m->stream));  // `offsets` and the caller's host arrays are released on return
-  if (m->kind == RL_RM || m->kind == RL_GLT) rc = build_distance_transform(m);
-  if (!rc && m->kind == RL_GLT) rc = glt_build(m);
-  if (m->kind == RL_CDDT || m->kind == RL_PCDDT) {
-    const bool was_pruned = m->pruned;
-    rc = cddt_build(m);
-    if (!rc && was_pruned) rc = cddt_prune(m, m->max_range);
-  }
-  return rc;
+  return refresh_structures(m);
 }
 
 int64_t rl_method_memory(const rl_method* m) {
@@ -561,6 +610,64 @@ int rl_eval_sensor_model(rl_method* m, const float* obs, const float* ranges, do
 int rl_calc_range_repeat_angles_eval_sensor_model(rl_method* m, const float* ins, const float* angles,
                                                   const float* obs, double* weights, int n, int M) {
   return run_cast(m, MODE_FUSED, ins, angles, obs, nullptr, weights, n, M);
+}
+
+// RangeMethod::calc_range_many_radial_optimized RangeLib.h:616-676 (loop constants :635-645 restated with the
+// reference's types: float step, double index_offset narrowed to float, roundf).
+int rl_calc_range_many_radial_optimized(rl_method* m, const float* ins, float* outs, int n, int num_rays,
+                                        float min_angle, float max_angle) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (n < 0 || num_rays < 2 || !std::isfinite(min_angle) || !std::isfinite(max_angle) || !(max_angle != min_angle)) {
+    set_error("calc_range_many_radial_optimized: need n >= 0, num_rays >= 2 and finite min_angle != max_angle");
+    return RL_E_INVALID;
+  }
+  if (n == 0) return RL_OK;
+  if (!ins || !outs) {
+    set_error("null data pointer");
+    return RL_E_INVALID;
+  }
+  if (m->radial_rays != num_rays || m->radial_min != min_angle || m->radial_max != max_angle) {
+    const float step = (max_angle - min_angle) / (num_rays - 1);
+    const int max_pair = (float)num_rays / 3.0;
+    const float index_offset_float = (num_rays - 1.0) * RL_PI / (max_angle - min_angle);
+    if (!(fabsf(index_offset_float) < 1e9f)) {
+      set_error("calc_range_many_radial_optimized: angular span too small for this beam count");
+      return RL_E_INVALID;
+    }
+    const int index_offset = roundf(index_offset_float);
+    const int count = std::min(std::max(max_pair + 1, index_offset), num_rays);
+    m->h_radial.resize(count);
+    float angle = min_angle;
+    for (int a = 0; a < count; ++a) {
+      m->h_radial[a] = angle;
+      angle += step;
+    }
+    if (m->radial_cap < count) {
+      RL_CUDA(cudaStreamSynchronize(m->stream));
+      cudaFree(m->d_radial);
+      m->d_radial = nullptr;
+      m->radial_cap = 0;
+      RL_CUDA(cudaMalloc(&m->d_radial, sizeof(float) * count));
+      m->radial_cap = count;
+    }
+    RL_CUDA(cudaMemcpyAsync(m->d_radial, m->h_radial.data(), sizeof(float) * count, cudaMemcpyHostToDevice, m->stream));
+    m->radial_rays = num_rays;
+    m->radial_min = min_angle;
+    m->radial_max = max_angle;
+    m->radial_count = count;
+    m->radial_pair = max_pair;
+    m->radial_offset = index_offset;
+  }
+  Marshal ms(m);
+  const int i_ins = ms.add(ins, sizeof(float) * 3 * (size_t)n, false);
+  const int i_out = ms.add_inout(outs, sizeof(float) * (size_t)n * num_rays);
+  rc = ms.prepare();
+  if (rc) return rc;
+  rc = launch_radial(m, (const float*)ms.dev(i_ins), m->d_radial, (float*)ms.dev(i_out), n, num_rays, m->radial_count,
+                     m->radial_pair, m->radial_offset);
+  if (rc) return rc;
+  return ms.finish();
 }
 
 int rl_calc_range_repeat_angles_eval_sensor_model_peers(rl_method* m, const float* ins, const float* angles,
@@ -668,6 +775,16 @@ int rl_method_peers_wait(rl_method* m) {
     return RL_E_STATE;
   }
   return launch_peers_wait(m);
+}
+
+int rl_debug_get_occ(rl_method* m, uint8_t* out) {
+  int rc = bind(m);
+  if (rc) return rc;
+  if (!out) return RL_E_INVALID;
+  const size_t n = (size_t)m->W * m->H;
+  if (n) RL_CUDA(cudaMemcpyAsync(out, m->d_occ, n, cudaMemcpyDeviceToHost, m->stream));
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  return RL_OK;
 }
 
 int rl_debug_get_dt(rl_method* m, float* out) {

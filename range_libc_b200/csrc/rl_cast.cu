@@ -420,6 +420,58 @@ __device__ __forceinline__ float cddt_cast(const MapView& mv, const CddtView& cv
   return -1.0f;  // the reference's assert(0) fall-through (:1514)
 }
 
+// CDDTCast::calc_range_pair RangeLib.h:1521-1649: the range along `heading` and the range along heading + pi from
+// one bin (the two neighbours of lx in the sorted bin).  Quirks kept: the non-flipped branch has no `first > lx`
+// early return and its occupied-cell test is a no-op (:1612, the pair is built and dropped); large bins use
+// lower_bound here where calc_range uses upper_bound (:1619 vs :1481).  The reference indexes the slice without a
+// bounds check (:1538-1539, undefined for a pose whose rotated y leaves the table); here that returns
+// (max_range, max_range).
+__device__ __forceinline__ float2 cddt_cast_pair(const MapView& mv, const CddtView& cv, float max_range, float x,
+                                                 float y, float heading) {
+  if (!finite3(x, y, heading)) return make_float2(max_range, max_range);
+  int a;
+  bool flipped;
+  cddt_discretize(cv, -heading, &a, &flipped);
+  const float ca = __ldg(cv.cosv + a), sa = __ldg(cv.sinv + a);
+  const float lx = fsub(fmul(x, ca), fmul(y, sa));
+  const float ly = fadd(fadd(fmul(x, sa), fmul(y, ca)), __ldg(cv.trans + a));
+  const unsigned li = (unsigned)f2i(ly);
+  if (li >= (unsigned)__ldg(cv.widths + a)) return make_float2(max_range, max_range);
+  const int64_t b = __ldg(cv.slice0 + a) + li;
+  const int64_t o0 = __ldg(cv.offsets + b), o1 = __ldg(cv.offsets + b + 1);
+  const float* __restrict__ B = cv.values + o0;
+  const int size = (int)(o1 - o0);
+  if (size == 0) return make_float2(max_range, max_range);
+  const float first = __ldg(B), last = __ldg(B + size - 1);
+  if (flipped) {
+    if (first > lx) return make_float2(max_range, fminf(max_range, fsub(first, lx)));  // :1552-1553
+    if (last < lx) return make_float2(fsub(lx, last), max_range);                      // :1554-1555
+    if (occ_at(mv, f2i(x), f2i(y))) return make_float2(0.0f, 0.0f);                    // :1559
+    int lo = 0, n = size;  // last element <= lx == upper_bound - 1 (:1566 and the scan :1569-1576)
+    while (n > 0) {
+      const int half = n >> 1;
+      const bool go_right = !(lx < __ldg(B + lo + half));
+      lo = go_right ? lo + half + 1 : lo;
+      n = go_right ? n - half - 1 : half;
+    }
+    const int index = lo - 1;
+    const float r = fsub(lx, __ldg(B + index));
+    if (index + 1 == size) return make_float2(r, max_range);
+    return make_float2(r, fsub(__ldg(B + index + 1), lx));
+  }
+  if (last < lx) return make_float2(max_range, fminf(max_range, fsub(lx, last)));  // :1605-1606
+  int lo = 0, n = size;  // first element >= lx (:1619 lower_bound and the scan :1623-1631)
+  while (n > 0) {
+    const int half = n >> 1;
+    const bool go_right = __ldg(B + lo + half) < lx;
+    lo = go_right ? lo + half + 1 : lo;
+    n = go_right ? n - half - 1 : half;
+  }
+  const float r = fsub(__ldg(B + lo), lx);
+  if (lo == 0) return make_float2(r, max_range);
+  return make_float2(r, fsub(lx, __ldg(B + lo - 1)));
+}
+
 // GiantLUTCast::calc_range RangeLib.h:1869-1880 with discretize_theta :1833-1867 (no flip, unlike CDDT)
 __device__ __forceinline__ float glt_cast(const MapView& mv, float max_range, float x, float y, float theta) {
   if (!finite3(x, y, theta)) return max_range;
@@ -525,6 +577,38 @@ cast_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float
       range = valid ? cast_one<KIND>(mv, cv, max_range, gx, gy, gth) : 0.0f;
     }
     if (valid) outs[r] = (MODE == MODE_GRID) ? range : fmul(range, xf.scale);
+  }
+}
+
+// RangeMethod::calc_range_many_radial_optimized RangeLib.h:616-676.  Row i of outs (num_rays floats) gets, for
+// a <= max_pair, the pair (range at beam a, range at beam a + index_offset) from one calc_range_pair, and for
+// max_pair < a < index_offset a plain calc_range; beams the reference never writes are left untouched.
+// `beam_angles[a]` is the reference's float accumulation min_angle + a * step, tabulated on the host.  A pair
+// whose second beam lands on a slot a later iteration of the reference overwrites (a + index_offset <= max_pair)
+// or outside the row (a + index_offset >= num_rays; the reference writes into the next row / past the buffer)
+// is dropped.  Methods without calc_range_pair return (-1, -1) from it (:419).
+template <int KIND>
+__global__ void __launch_bounds__(256, 4)
+radial_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float* __restrict__ ins,
+              const float* __restrict__ beam_angles, float* __restrict__ outs, long long total, int num_rays, int count,
+              int max_pair, int index_offset) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += stride) {
+    const long long i = r / count;
+    const int a = (int)(r - i * count);
+    float x, y, th;
+    world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
+    th = fsub(th, __ldg(beam_angles + a));
+    float* row = outs + i * num_rays;
+    if (a <= max_pair) {
+      float2 pr = make_float2(-1.0f, -1.0f);
+      if (KIND == RL_CDDT) pr = cddt_cast_pair(mv, cv, max_range, y, x, th);
+      if (a < num_rays) row[a] = fmul(pr.x, xf.scale);
+      const int b = a + index_offset;
+      if (b > max_pair && b >= 0 && b < num_rays) row[b] = fmul(pr.y, xf.scale);
+    } else if (a < num_rays) {
+      row[a] = fmul(cast_one<KIND>(mv, cv, max_range, y, x, th), xf.scale);
+    }
   }
 }
 
@@ -935,6 +1019,28 @@ int launch_cast(rl_method* m, int mode, const float* ins, const float* angles, c
     case RL_GLT: return launch_cast_kind<RL_GLT>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
     default: return launch_cast_kind<RL_CDDT>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
   }
+}
+
+int launch_radial(rl_method* m, const float* ins, const float* beam_angles, float* outs, int n, int num_rays, int count,
+                  int max_pair, int index_offset) {
+  const long long total = (long long)n * count;
+  if (total <= 0) return RL_OK;
+  const MapView mv = m->map_view();
+  const CddtView cv = m->cddt_view();
+  const int grid = (int)min((total + 255) / 256, (long long)sm_count() * 32);
+#define RL_LAUNCH_RADIAL(K) \
+  radial_kernel<K><<<grid, 256, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, beam_angles, outs, total, num_rays, \
+                                               count, max_pair, index_offset)
+  switch (m->kind) {
+    case RL_BL: RL_LAUNCH_RADIAL(RL_BL); break;
+    case RL_RM: RL_LAUNCH_RADIAL(RL_RM); break;
+    case RL_GLT: RL_LAUNCH_RADIAL(RL_GLT); break;
+    default: RL_LAUNCH_RADIAL(RL_CDDT); break;
+  }
+#undef RL_LAUNCH_RADIAL
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
 }
 
 int launch_eval_sensor(rl_method* m, const float* obs, const float* ranges, double* outs, int M, int n) {

@@ -160,6 +160,12 @@ struct rl_method {
   void* h_stage = nullptr;      // pinned + mapped
   void* h_stage_dev = nullptr;  // its device alias (zero-copy)
   size_t h_stage_bytes = 0;
+  // calc_range_many_radial_optimized: beam-angle table of the last call
+  float* d_radial = nullptr;
+  int radial_cap = 0, radial_rays = -1, radial_count = 0;
+  float radial_min = 0.f, radial_max = 0.f;
+  int radial_pair = 0, radial_offset = 0;
+  std::vector<float> h_radial;
 
   size_t dt_elems() const { return (size_t)W * H; }
   int coop_threshold = 16;
@@ -186,6 +192,8 @@ int build_distance_transform(rl_method* m);
 // rl_occ.cu
 int upload_occupancy(rl_method* m, const rl_map* map);
 int apply_patch(rl_method* m, const uint8_t* d_patch, int x0, int y0, int w, int h);
+int ingest_occupancy_grid(rl_method* m, const int8_t* d_data);
+int ingest_rgba(rl_method* m, const uint8_t* d_rgba, float threshold);
 int apply_patch_batch(rl_method* m, const uint8_t* d_patches, const int* d_rects, const long long* d_offsets, int n);
 // rl_cddt.cu
 int cddt_build(rl_method* m);
@@ -194,6 +202,8 @@ void cddt_free(rl_method* m);
 // rl_cast.cu -- the batched query kernels (all kinds, all modes)
 int launch_cast(rl_method* m, int mode, const float* d_ins, const float* d_angles, const float* d_obs, float* d_outs,
                 double* d_weights, int n, int num_angles, const PeerOut* peers = nullptr);
+int launch_radial(rl_method* m, const float* d_ins, const float* d_beam_angles, float* d_outs, int n, int num_rays,
+                  int count, int max_pair, int index_offset);
 int launch_eval_sensor(rl_method* m, const float* d_obs, const float* d_ranges, double* d_outs, int m_rays, int n);
 int launch_sincosf(const float* d_x, float* d_s, float* d_c, int n, cudaStream_t st);
 int launch_peers_wait(rl_method* m);

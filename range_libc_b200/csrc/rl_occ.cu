@@ -2,6 +2,8 @@
 // RangeLib.h:126) plus a bit-packed copy in 8x8-cell tiles (one 64-bit word per tile) that the BL
 // walk and the CDDT/BL "standing on an obstacle" test read.  Dynamic maps (BASELINE config 4)
 // patch both on the device.
+#include <algorithm>
+
 #include "rl_internal.cuh"
 
 namespace rl {
@@ -102,6 +104,74 @@ int apply_patch(rl_method* m, const uint8_t* d_patch, int x0, int y0, int w, int
   count_launch();
   RL_CHECK_LAUNCH();
   return RL_OK;
+}
+
+// ---- whole-map ingest on the device: the map never visits the host ----
+
+// ROS nav_msgs/OccupancyGrid data (int8, row-major [rows][cols]; 0 free, -1 unknown, 100 blocked) as the
+// reference's PyOMap(OccupancyGrid) reads it (RangeLibc.pyx:146-157): OMap(rows, cols) with
+// grid[x][y] = data[x*cols + y] > 10 -- the message's row index is the map's x, so the layout already is x-major.
+__global__ void ingest_grid_kernel(const int8_t* __restrict__ data, uint8_t* __restrict__ occ, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) occ[i] = data[i] > 10 ? 1 : 0;
+}
+
+// RGBA8 image rows (as lodepng_decode32 returns them) -> occupancy, the reference's OMap(filename, threshold)
+// loop (RangeLib.h:189-199): r = byte 2, g = byte 1, b = byte 0, gray = (int)rgb2gray(r,g,b) with rgb2gray's
+// double sum narrowed to its float return type (RangeUtils.h:30-32), occupied iff gray < threshold.
+// The image is row-major [H][W] and the grid x-major [W][H]: 32x32 tiles are transposed through shared memory
+// so both the pixel reads and the cell writes are coalesced.
+__global__ void ingest_rgba_kernel(const uchar4* __restrict__ img, uint8_t* __restrict__ occ, int W, int H,
+                                   float threshold) {
+  __shared__ uint8_t tile[32][33];
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int x = x0 + threadIdx.x, y = y0 + j;
+    uint8_t o = 0;
+    if (x < W && y < H) {
+      const uchar4 p = __ldg(img + (size_t)y * W + x);
+      const double r = (double)(float)(int)p.z, g = (double)(float)(int)p.y, b = (double)(float)(int)p.x;
+      const float grayf = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(0.229, r), __dmul_rn(0.587, g)), __dmul_rn(0.114, b)));
+      const int gray = __float2int_rz(grayf);
+      o = ((float)gray < threshold) ? 1 : 0;
+    }
+    tile[j][threadIdx.x] = o;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int x = x0 + i, y = y0 + threadIdx.x;
+    if (x < W && y < H) occ[(size_t)x * H + y] = tile[threadIdx.x][i];
+  }
+}
+
+static int repack_all(rl_method* m) {
+  const long long tiles = (long long)m->tiles8_x() * m->tiles8_y();
+  if (tiles <= 0) return RL_OK;
+  pack_tiles_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, m->stream>>>(m->d_occ, m->d_bits_t, m->W, m->H,
+                                                                          m->tiles8_y(), 0, m->tiles8_x(), 0,
+                                                                          m->tiles8_y());
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
+}
+
+int ingest_occupancy_grid(rl_method* m, const int8_t* d_data) {
+  const size_t n = (size_t)m->W * m->H;
+  if (n == 0) return RL_OK;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)148 * 16);
+  ingest_grid_kernel<<<grid, 256, 0, m->stream>>>(d_data, m->d_occ, n);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return repack_all(m);
+}
+
+int ingest_rgba(rl_method* m, const uint8_t* d_rgba, float threshold) {
+  if ((size_t)m->W * m->H == 0) return RL_OK;
+  const dim3 grid((m->W + 31) / 32, (m->H + 31) / 32), block(32, 8);
+  ingest_rgba_kernel<<<grid, block, 0, m->stream>>>((const uchar4*)d_rgba, m->d_occ, m->W, m->H, threshold);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return repack_all(m);
 }
 
 }  // namespace rl

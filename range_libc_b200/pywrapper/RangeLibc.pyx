@@ -12,6 +12,7 @@ Same classes and methods a particle filter written against the reference uses:
       .calc_range_many(ins[N,3], outs[N])
       .calc_range_repeat_angles(ins[N,3], angles[M], outs[N*M])
       .calc_range_repeat_angles_eval_sensor_model(ins, angles, obs[M], weights[N])
+      .calc_range_many_radial_optimized(num_rays, min_angle, max_angle, ins, outs[N*num_rays])
       .eval_sensor_model(obs, ranges, outs, num_rays, num_particles)
       .set_sensor_model(table[K,K])
 
@@ -51,6 +52,8 @@ cdef extern from "rangelib_b200.h":
     int rl_eval_sensor_model(rl_method* m, const float* obs, const float* ranges, double* outs, int k, int n)
     int rl_calc_range_repeat_angles_eval_sensor_model(rl_method* m, const float* ins, const float* angles,
                                                       const float* obs, double* weights, int n, int k)
+    int rl_calc_range_many_radial_optimized(rl_method* m, const float* ins, float* outs, int n, int num_rays,
+                                            float min_angle, float max_angle)
 
 # the reference exports its compile-time switches; keep the names importable
 USE_CACHED_TRIG = False
@@ -192,6 +195,15 @@ cdef class _Method:
             raise ValueError("shape mismatch")
         _ck(rl_calc_range_repeat_angles_eval_sensor_model(self.ptr, &ins[0, 0], &angles[0], &obs[0], &weights[0],
                                                           <int>ins.shape[0], <int>angles.shape[0]))
+
+    cpdef calc_range_many_radial_optimized(self, int num_rays, float min_angle, float max_angle, float[:, ::1] ins,
+                                           float[::1] outs):
+        if ins.shape[0] == 0:
+            return
+        if ins.shape[1] != 3 or outs.shape[0] < ins.shape[0] * num_rays:
+            raise ValueError("shape mismatch")
+        _ck(rl_calc_range_many_radial_optimized(self.ptr, &ins[0, 0], &outs[0], <int>ins.shape[0], num_rays, min_angle,
+                                                max_angle))
 
     cpdef eval_sensor_model(self, float[::1] observation, float[::1] ranges, double[::1] outs, int num_rays,
                             int num_particles):

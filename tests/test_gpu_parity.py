@@ -489,3 +489,93 @@ def test_bl_persistent_kernel_matches_one_ray_per_thread():
     out2 = np.empty_like(out)
     meth.calc_range_repeat_angles(parts, angles, out2)
     assert_bit_equal(out2, out, "persistent vs one-ray-per-thread")
+
+
+@pytest.mark.parametrize("kn", ["bl", "rm", "cddt", "pcddt"])
+def test_radial_optimized(kn):
+    """calc_range_many_radial_optimized (RangeLib.h:616-676; pairs from CDDTCast::calc_range_pair :1521-1649):
+    bit-exact against the reference's golden vectors, including the beams the reference leaves unwritten, for
+    host and device pointers; then against the oracle on a larger fresh batch."""
+    import os
+    import torch
+    from helpers import GOLD
+    g = np.load(os.path.join(GOLD, "vectors_radial.npz"))
+    for name in ("basement_hallways_10cm", "basement_hallways_5cm"):
+        occ = wl.load_map(name)
+        for wname in ("id", "rot"):
+            meth = make(kn, occ, world=world_tuple(g["world_rot"]) if wname == "rot" else None)
+            ins = g[name + "/particles"] if wname == "id" else g[name + "/particles_rot"]
+            for ci, (n, lo, hi) in enumerate(g["configs"]):
+                n = int(n)
+                want = g["%s/%s/%s/%d" % (name, kn, wname, ci)]
+                outs = np.full(len(ins) * n, g["fill"], np.float32)
+                meth.calc_range_many_radial_optimized(n, float(lo), float(hi), ins, outs)
+                assert_bit_equal(outs, want, "%s %s %s cfg %d host" % (name, kn, wname, ci))
+                d_out = torch.full((len(ins) * n,), float(g["fill"]), dtype=torch.float32, device="cuda")
+                meth.calc_range_many_radial_optimized(n, float(lo), float(hi), torch.from_numpy(ins).cuda(), d_out)
+                torch.cuda.synchronize()
+                assert_bit_equal(d_out.cpu().numpy(), want, "%s %s %s cfg %d device" % (name, kn, wname, ci))
+    occ = wl.load_map("basement_hallways_5cm")
+    parts = wl.pf_particles_uniform(occ, 3000, seed=77)
+    meth = make(kn, occ)
+    o = port.Oracle(KINDS[kn], occ, MR, TD)
+    for n, lo, hi in ((1081, -2.35619449615, 2.35619449615), (54, -0.75 * np.pi, 0.75 * np.pi)):
+        got = np.full(len(parts) * n, -3.0, np.float32)
+        want = got.copy()
+        meth.calc_range_many_radial_optimized(n, lo, hi, parts, got)
+        o.calc_range_many_radial_optimized(n, lo, hi, parts, want)
+        assert_bit_equal(got, want, "%s fresh %d beams" % (kn, n))
+    with pytest.raises(rl.RangeLibError):
+        meth.calc_range_many_radial_optimized(1, 0.0, 1.0, parts, got)
+    with pytest.raises(rl.RangeLibError):
+        meth.calc_range_many_radial_optimized(10, 1.0, 1.0, parts, got)
+
+
+def test_device_map_ingest_rgba_and_occupancy_grid():
+    """Whole-map ingest on the device.  The RGBA conversion is checked exhaustively -- a 4096 x 4096
+    image holds every (r, g, b) triple once -- against the host mirror of the reference's OMap(png, threshold)
+    (mapio.occupancy_from_rgba, itself pinned to the reference's loader in the CPU suite); structures rebuilt from
+    the ingested map equal those of a handle constructed from the same occupancy."""
+    import torch
+    from range_libc_b200 import mapio
+    side = 4096
+    v = np.arange(side * side, dtype=np.uint32)
+    rgba = np.empty((side, side, 4), np.uint8)
+    rgba[..., 0] = (v & 255).reshape(side, side)
+    rgba[..., 1] = ((v >> 8) & 255).reshape(side, side)
+    rgba[..., 2] = ((v >> 16) & 255).reshape(side, side)
+    rgba[..., 3] = 255
+    for thr in (128.0, 37.5):
+        want = mapio.occupancy_from_rgba(rgba, thr)  # [W, H] x-major
+        bl = rl.PyBresenhamsLine(rl.PyOMap(side, side), MR)
+        bl.set_map_rgba(torch.from_numpy(rgba).cuda(), thr)
+        assert np.array_equal(bl.occupancy(), want), "rgba ingest, threshold %g" % thr
+    # non-square, non-multiple-of-32 image, host pointer; RM rebuilds its distance transform
+    rng = np.random.default_rng(8)
+    rows, cols = 301, 517  # image rows = map height, cols = map width
+    img = rng.integers(0, 256, (rows, cols, 4), dtype=np.uint8)
+    img[rng.random((rows, cols)) < 0.9] = 255
+    occ = mapio.occupancy_from_rgba(img, 128.0)
+    assert occ.shape == (cols, rows)
+    rm = rl.PyRayMarchingGPU(rl.PyOMap(cols, rows), MR)
+    rm.set_map_rgba(img)
+    fresh = make("rm", occ)
+    assert_bit_equal(rm.distance_transform(), fresh.distance_transform(), "distance transform after rgba ingest")
+    q = wl.random_queries(cols, rows, 20000, seed=3)
+    a, b = np.empty(len(q), np.float32), np.empty(len(q), np.float32)
+    rm.calc_range_many_grid(q, a)
+    fresh.calc_range_many_grid(q, b)
+    assert_bit_equal(a, b, "ranges after rgba ingest")
+    # OccupancyGrid data: int8 [rows = map width][cols = map height], occupied iff > 10
+    data = rng.choice(np.array([-1, 0, 5, 10, 11, 100], np.int8), size=(cols, rows), p=[.2, .6, .05, .05, .05, .05])
+    occ2 = (data > 10).astype(np.uint8)
+    for src in (data, torch.from_numpy(data).cuda()):
+        cd = rl.PyCDDTCast(rl.PyOMap(cols, rows), MR, TD)
+        cd.prune()
+        cd.set_map_occupancy_grid(src)
+        fresh = make("pcddt", occ2)
+        cd.calc_range_many_grid(q, a)
+        fresh.calc_range_many_grid(q, b)
+        assert_bit_equal(a, b, "PCDDT ranges after occupancy-grid ingest")
+    with pytest.raises(rl.RangeLibError):
+        cd.set_map_occupancy_grid(data[:-1])

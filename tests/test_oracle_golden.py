@@ -61,3 +61,24 @@ def test_restated_glibc_trig_matches_libm_sample():
     lo = int(np.float32(1.0).view(np.uint32))
     hi = int(np.float32(8.0).view(np.uint32))
     assert port.trig_compare(lo, hi, 7) == (0, 0)
+
+
+@pytest.mark.parametrize("name", ["basement_hallways_10cm", "basement_hallways_5cm"])
+@pytest.mark.parametrize("kn", ["bl", "rm", "cddt", "pcddt"])
+def test_radial_optimized_matches_reference_vectors(name, kn):
+    """calc_range_many_radial_optimized + CDDTCast::calc_range_pair (RangeLib.h:616-676, :1521-1649) against
+    tests/golden/vectors_radial.npz (made by the unmodified reference, make_golden_radial.py)."""
+    import os
+    from helpers import GOLD
+    g = np.load(os.path.join(GOLD, "vectors_radial.npz"))
+    occ = wl.load_map(name)
+    for wname in ("id", "rot"):
+        o = port.Oracle(KINDS[kn], occ, 500.0, 108)
+        if wname == "rot":
+            o.set_world(*world_tuple(g["world_rot"]))
+        ins = g[name + "/particles"] if wname == "id" else g[name + "/particles_rot"]
+        for ci, (n, lo, hi) in enumerate(g["configs"]):
+            n = int(n)
+            outs = np.full(len(ins) * n, g["fill"], np.float32)
+            o.calc_range_many_radial_optimized(n, float(lo), float(hi), ins, outs)
+            assert_bit_equal(outs, g["%s/%s/%s/%d" % (name, kn, wname, ci)], "%s %s cfg %d" % (kn, wname, ci))
