@@ -561,6 +561,27 @@ def extra_throughput(rl, wl, occ, omap, dev, stream, peak):
             out[nm + "_error"] = str(ex)[:200]
     out["workload"] = "2^24 uniformly random grid-coordinate queries on %s (BL: 2^22), max_range 500, device resident" % MAP
     del q, r
+    # lidar-scan batches through calc_range_repeat_angles (numpy_calc_range_angles): the beams of one pose are
+    # neighbours in a warp, so their distance-map reads share 128-byte lines -- unlike the uniformly random rays
+    # above, whose rate is capped by L1 tag lookups (one line per clock per SM, 290 G lines/s chip-wide)
+    try:
+        rm = rl.PyRayMarchingGPU(omap, MAX_RANGE)
+        rm.set_stream(stream.cuda_stream)
+        scans = {}
+        dt_host = rm.distance_transform()
+        for label, n_p, n_b, maker in (("uniform_262144x60", 262144, 60, wl.pf_particles_uniform),
+                                       ("tracking_262144x60", 262144, 60, lambda o, n, seed: wl.pf_particles_tracking(o, n, seed=seed, dt=dt_host)[0]),
+                                       ("uniform_16384x1080", 16384, 1080, wl.pf_particles_uniform)):
+            parts = torch.from_numpy(maker(occ, n_p, seed=11)).to(dev)
+            ang = torch.from_numpy(wl.lidar_angles(n_b)).to(dev)
+            ranges = torch.empty(n_p * n_b, dtype=torch.float32, device=dev)
+            t = _time_launches(lambda: rm.calc_range_repeat_angles(parts, ang, ranges), stream)
+            scans[label] = {"rays_per_s": n_p * n_b / t, "hbm_frac": (12.0 * n_p + 4.0 * n_b + 4.0 * n_p * n_b) / t / 1e9 / peak}
+            del parts, ang, ranges
+        out["rm_scan_batches"] = scans
+        del rm
+    except Exception as ex:  # noqa: BLE001
+        out["rm_scan_error"] = str(ex)[:200]
     # C3: CDDT / PCDDT on gigantic_map (10976^2), theta_discretization 108
     try:
         big = wl.load_map("gigantic_map")

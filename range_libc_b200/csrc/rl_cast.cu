@@ -819,98 +819,177 @@ bl_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
 // contiguous chunk of rays.  It alternates between
 //   setup   all 32 lanes convergent: load pose, world->grid, (double-precision) sin/cos for the
 //           next 128 rays of the chunk, parked as (x0, y0, dx, dy) in shared memory, and
-//   march   one sphere-tracing step for every lane that holds a ray; a lane whose ray ended
-//           writes its range and immediately takes the next parked ray.
+//   march   a burst of sphere-tracing steps for every lane that holds a ray; a lane whose ray ended
+//           writes its range and takes the next parked ray.
 // In-flight rays keep their state in registers across a setup phase, so nothing drains between
-// batches and the marching loop runs with ~all lanes busy until the chunk is exhausted.
+// batches and the marching loop runs with most lanes busy until the chunk is exhausted.
 // ------------------------------------------------------------------------------------------
 #define RL_QB 4  // parked rays per lane and setup phase
-#ifndef RL_PERSIST_BURST
-#define RL_PERSIST_BURST 4
+#ifndef RL_RM_BURST_PAIRS
+#define RL_RM_BURST_PAIRS 3  // sphere-tracing steps per refill round = 2 * this
 #endif
 
-template <int MODE>
-__global__ void __launch_bounds__(256, 6)
+// ------------------------------------------------------------------------------------------
+// Shape of the marching loop (round-1 ncu source view of the first version of this kernel: 19 % of all issued
+// warp-instructions were the hit epilogue -- int->float, squares, sqrt -- run inside the stepping loop for an
+// average of 2.4 lanes; another ~8 % were BSSY/BSYNC/branch bookkeeping of the loop's three exits; and 45 % of
+// the stall samples sat on the instruction after the distance load).
+//  * The stepping burst is straight-line predicated code: a lane whose ray has ended keeps its t (which, by
+//    construction, reproduces the end condition: t >= max_range, or the out-of-map / obstacle cell at
+//    (int)(x0 + dx t), (int)(y0 + dy t)) and simply stops loading; no branch, no reconvergence point.
+//  * The epilogue runs once per refill round for all lanes that ended in the burst, classifying from t alone.
+//  * SLOTS rays per lane are marched interleaved (independent dependent-load chains), which doubles the loads
+//    in flight per warp at the same occupancy.
+// Arithmetic per step is rm_step's, i.e. the reference's.
+// ------------------------------------------------------------------------------------------
+struct RmSlot {
+  float x0, y0, dx, dy, t;
+  int id;
+  bool busy;   // the slot holds a ray (marching, or ended and not yet written out)
+  bool alive;  // ... and it is still marching
+};
+
+template <bool COND_LOAD>
+__device__ __forceinline__ void rm_step_pred(const float* __restrict__ dt, unsigned W, unsigned H, float max_range,
+                                             RmSlot& r) {
+  const int px = __float2int_rz(fadd(r.x0, fmul(r.dx, r.t)));
+  const int py = __float2int_rz(fadd(r.y0, fmul(r.dy, r.t)));
+  const bool go = r.alive && (unsigned)px < W && (unsigned)py < H;
+  // COND_LOAD: lanes that are not marching issue no load (ptxas makes it a BSSY / BRA / BSYNC triple, three
+  // more instructions per step); otherwise they read cell 0 and ignore it (one more 128-byte line in the
+  // request -- the gather rate of this kernel is bounded by L1 tag lookups, one line per clock per SM)
+  float d = 0.0f;
+  if (COND_LOAD) {
+    if (go) d = __ldg(dt + ((unsigned)px * H + (unsigned)py));
+  } else {
+    d = __ldg(dt + (go ? (unsigned)px * H + (unsigned)py : 0u));
+  }
+  const bool adv = go && !(d <= 0.0f);
+  const float tn = fadd(r.t, fmaxf(fmul(d, 0.999f), 1.0f));
+  r.t = adv ? tn : r.t;
+  r.alive = adv && (tn < max_range);
+}
+
+// result of a ray that ended with parameter t (see above); RangeLib.h:938-961
+__device__ __forceinline__ float rm_result(unsigned W, unsigned H, float max_range, const RmSlot& r) {
+  if (!(r.t < max_range)) return max_range;
+  const int px = __float2int_rz(fadd(r.x0, fmul(r.dx, r.t)));
+  const int py = __float2int_rz(fadd(r.y0, fmul(r.dy, r.t)));
+  if ((unsigned)px >= W || (unsigned)py >= H) return max_range;
+  const float xd = fsub((float)px, r.x0), yd = fsub((float)py, r.y0);
+  return __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
+}
+
+// PARK_REGS: the rays set up ahead of the march are parked one per lane in registers and handed out with
+// shuffles, instead of RL_QB per lane in shared memory: the kernel then uses no shared memory at all and the
+// whole 256 KB of the SM serves as L1 for the distance-map gathers (which are what bounds it: ncu shows the
+// L1 -> crossbar miss-request interface busy 85 % of the active cycles, one missing sector per clock per SM).
+template <int MODE, int SLOTS, bool COND_LOAD, bool PARK_REGS>
+__global__ void __launch_bounds__(256, SLOTS == 1 ? 6 : 4)
 rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __restrict__ ins,
-                  const float* __restrict__ angles, float* __restrict__ outs, long long total, int M, int chunk) {
-  __shared__ float4 q_all[8 * RL_QB * 32];
+                  const float* __restrict__ angles, float* __restrict__ outs, long long total, int M, int chunk,
+                  int burst_pairs) {
+  constexpr int PARKED = PARK_REGS ? 32 : RL_QB * 32;  // rays per setup phase
+  __shared__ float4 q_all[PARK_REGS ? 1 : 8 * RL_QB * 32];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float4* q = q_all + wib * (RL_QB * 32);
+  float4* q = q_all + (PARK_REGS ? 0 : wib * (RL_QB * 32));
+  float4 parked = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
   const long long begin = warp_global * chunk;
   const long long end = min(begin + (long long)chunk, total);
   if (begin >= end) return;
   const float out_scale = (MODE == MODE_GRID) ? 1.0f : xf.scale;
+  const float* __restrict__ dt = mv.dt;
+  const unsigned W = (unsigned)mv.W, H = (unsigned)mv.H;
 
-  // all ray bookkeeping is relative to `begin` (chunk <= 2^20) to keep the state in 32-bit registers
-  const int count = (int)(end - begin);
-  int next_setup = 0;  // first ray of the chunk that has not been set up yet
-  int batch_base = 0;  // ray of q[0]
-  int batch_n = 0, batch_pos = 0;
-
-  bool active = false;
-  int id = 0;
-  float x0 = 0.f, y0 = 0.f, dx = 0.f, dy = 0.f, t = 0.f;
+  const int count = (int)(end - begin);  // bookkeeping relative to `begin` (chunk <= 2^20)
+  int next_setup = 0, batch_base = 0, batch_n = 0, batch_pos = 0;
+  RmSlot r[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    r[s].x0 = r[s].y0 = r[s].dx = r[s].dy = r[s].t = 0.f;
+    r[s].id = 0;
+    r[s].busy = r[s].alive = false;
+  }
 
   while (true) {
-    const unsigned idle = __ballot_sync(FULL, !active);
-    if (idle) {
-      if (batch_pos == batch_n && next_setup < count) {
-        // ---- setup phase (warp-uniform branch) ----
-        __syncwarp();
-        batch_base = next_setup;
-        batch_n = min(RL_QB * 32, count - next_setup);
-        batch_pos = 0;
-        for (int e = lane; e < batch_n; e += 32) {
-          const long long r = begin + batch_base + e;
-          float gx, gy, gth;
-          load_pose<MODE>(xf, ins, angles, r, M, &gx, &gy, &gth);
-          float4 ray;
-          if (finite3(gx, gy, gth)) {
-            float sn, cs;
-            rl_sincosf(gth, &sn, &cs);
-            ray = make_float4(gx, gy, cs, sn);
-          } else {
-            ray = make_float4(-1e30f, 0.f, 0.f, 0.f);  // leaves the map on the first step -> max_range
+    bool any_busy = false;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      // with 32 parked rays a refill can exhaust them and still leave lanes idle: a second pass sets up more
+#pragma unroll
+      for (int pass = 0; pass < (PARK_REGS ? 2 : 1); ++pass) {
+        const unsigned idle = __ballot_sync(FULL, !r[s].busy);
+        if (idle) {
+          if (batch_pos == batch_n && next_setup < count) {
+            // ---- setup phase (warp-uniform branch): pose -> (x0, y0, cos, sin) for the next PARKED rays ----
+            __syncwarp();
+            batch_base = next_setup;
+            batch_n = min(PARKED, count - next_setup);
+            batch_pos = 0;
+            for (int e = lane; e < batch_n; e += 32) {
+              float gx, gy, gth;
+              load_pose<MODE>(xf, ins, angles, begin + batch_base + e, M, &gx, &gy, &gth);
+              float sn = 0.f, cs = 0.f;
+              const bool ok = finite3(gx, gy, gth);
+              if (ok) rl_sincosf(gth, &sn, &cs);
+              // a non-finite pose leaves the map on its first step -> max_range
+              const float4 ray = ok ? make_float4(gx, gy, cs, sn) : make_float4(-1e30f, 0.f, 0.f, 0.f);
+              if (PARK_REGS) parked = ray; else q[e] = ray;
+            }
+            next_setup += batch_n;
+            __syncwarp();
           }
-          q[e] = ray;
+          const int avail = batch_n - batch_pos;
+          if (avail > 0) {
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            const bool take = !r[s].busy && rank < avail;
+            float4 ray;
+            if (PARK_REGS) {
+              const int src = (batch_pos + rank) & 31;
+              ray.x = __shfl_sync(FULL, parked.x, src);
+              ray.y = __shfl_sync(FULL, parked.y, src);
+              ray.z = __shfl_sync(FULL, parked.z, src);
+              ray.w = __shfl_sync(FULL, parked.w, src);
+            } else if (take) {
+              ray = q[batch_pos + rank];
+            }
+            if (take) {
+              r[s].x0 = ray.x; r[s].y0 = ray.y; r[s].dx = ray.z; r[s].dy = ray.w;
+              r[s].t = 0.0f;
+              r[s].id = batch_base + batch_pos + rank;
+              r[s].busy = r[s].alive = true;
+            }
+            batch_pos += min(avail, __popc(idle));
+          }
         }
-        next_setup += batch_n;
-        __syncwarp();
       }
-      const int avail = batch_n - batch_pos;
-      if (avail > 0) {
-        const int rank = __popc(idle & ((1u << lane) - 1u));
-        if (!active && rank < avail) {
-          const float4 ray = q[batch_pos + rank];
-          x0 = ray.x; y0 = ray.y; dx = ray.z; dy = ray.w;
-          t = 0.0f;
-          id = batch_base + batch_pos + rank;
-          active = true;
-        }
-        batch_pos += min(avail, __popc(idle));
+      any_busy = any_busy || r[s].busy;
+    }
+    if (!__any_sync(FULL, any_busy)) break;
+
+#pragma unroll 1
+    for (int b = 0; b < burst_pairs; ++b) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) rm_step_pred<COND_LOAD>(dt, W, H, max_range, r[s]);
       }
     }
-    if (!__any_sync(FULL, active)) break;
-    if (active) {
-      // a short burst of iterations of RayMarching::calc_range's loop (RangeLib.h:938-959) between two
-      // re-queuing rounds: the refill bookkeeping (~25 instructions) is paid once per burst
-      float result;
-      bool done;
-      int burst = RL_PERSIST_BURST;
-      do {
-        done = rm_step(mv, max_range, x0, y0, dx, dy, t, result);
-      } while (!done && --burst);
-      if (done) {
+
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      if (r[s].busy && !r[s].alive) {
+        const float result = rm_result(W, H, max_range, r[s]);
         if (MODE == MODE_GLT_BUILD) {
           // r = min(max_range, r); uint16 val = r * limits_div_max (RangeLib.h:1804-1806); xf.scale carries the factor
           const float rr = (result < max_range) ? result : max_range;
-          ((uint16_t*)outs)[begin + id] = (uint16_t)__float2int_rz(fmul(rr, xf.scale));
+          ((uint16_t*)outs)[begin + r[s].id] = (uint16_t)__float2int_rz(fmul(rr, xf.scale));
         } else {
-          outs[begin + id] = (MODE == MODE_GRID) ? result : fmul(result, out_scale);
+          outs[begin + r[s].id] = (MODE == MODE_GRID) ? result : fmul(result, out_scale);
         }
-        active = false;
+        r[s].busy = false;
       }
     }
   }
@@ -980,18 +1059,31 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
       RL_CHECK_LAUNCH();
       return RL_OK;
     }
-    const long long resident_warps = (long long)sm_count() * 48;
-    if (KIND == RL_RM && m->max_range > 0.0f && total >= resident_warps * 64 && m->persist) {
+    // RL_RM_PERSIST (tuning / A-B; measured on 2^24 random rays, basement_hallways_5cm):
+    //   0 off | 1 default: parked rays in registers, unconditional load (39.6 G rays/s) | 2 the same with a
+    //   conditional load (39.1) | 3 parked rays in shared memory (37.3) | 4 = 3 with two rays per lane (36.9)
+    static const int rm_persist_env = getenv("RL_RM_PERSIST") ? atoi(getenv("RL_RM_PERSIST")) : -1;
+    static const int rm_burst_pairs = getenv("RL_RM_BURST_PAIRS") ? max(1, atoi(getenv("RL_RM_BURST_PAIRS"))) : RL_RM_BURST_PAIRS;
+    const int variant = rm_persist_env >= 0 ? rm_persist_env : m->persist;
+    const long long resident_warps = (long long)sm_count() * (variant == 4 ? 32 : 48);
+    if (KIND == RL_RM && m->max_range > 0.0f && total >= resident_warps * 64 && variant) {
       long long per_warp = (total + resident_warps - 1) / resident_warps;
       const int chunk = (int)min((long long)1 << 20, ((per_warp + 31) / 32) * 32);
       const long long warps = (total + chunk - 1) / chunk;
       const int grid = (int)((warps + 7) / 8);
-#define RL_LAUNCH_PERSIST(MD) \
-  rm_persist_kernel<MD><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk)
+#define RL_PERSIST_ARGS <<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, rm_burst_pairs)
+#define RL_LAUNCH_PERSIST(MD)                                                      \
+  do {                                                                             \
+    if (variant == 2) rm_persist_kernel<MD, 1, true, true> RL_PERSIST_ARGS;        \
+    else if (variant == 3) rm_persist_kernel<MD, 1, false, false> RL_PERSIST_ARGS; \
+    else if (variant == 4) rm_persist_kernel<MD, 2, true, false> RL_PERSIST_ARGS;  \
+    else rm_persist_kernel<MD, 1, false, true> RL_PERSIST_ARGS;                    \
+  } while (0)
       if (mode == MODE_GRID) RL_LAUNCH_PERSIST(MODE_GRID);
       else if (mode == MODE_WORLD) RL_LAUNCH_PERSIST(MODE_WORLD);
       else RL_LAUNCH_PERSIST(MODE_ANGLES);
 #undef RL_LAUNCH_PERSIST
+#undef RL_PERSIST_ARGS
       count_launch();
       RL_CHECK_LAUNCH();
       return RL_OK;
@@ -1081,8 +1173,9 @@ int glt_build(rl_method* m) {
   const int chunk = (int)min((long long)1 << 20, ((per_warp + 31) / 32) * 32);
   const long long warps = (total + chunk - 1) / chunk;
   const int grid = (int)((warps + 7) / 8);
-  rm_persist_kernel<MODE_GLT_BUILD><<<grid, 256, 0, m->stream>>>(mv, xf, m->max_range, nullptr, nullptr, (float*)m->d_glt,
-                                                               total, (int)m->td, chunk);
+  rm_persist_kernel<MODE_GLT_BUILD, 1, false, true><<<grid, 256, 0, m->stream>>>(mv, xf, m->max_range, nullptr, nullptr,
+                                                                        (float*)m->d_glt, total, (int)m->td, chunk,
+                                                                        RL_RM_BURST_PAIRS);
   count_launch();
   RL_CHECK_LAUNCH();
   return RL_OK;

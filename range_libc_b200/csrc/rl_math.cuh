@@ -37,13 +37,13 @@ __device__ __forceinline__ float sc_sin_poly(double x, double x2) {
   double s = __dadd_rn(x, __dmul_rn(x3, RL_SC_S1));
   return __double2float_rn(__dadd_rn(s, __dmul_rn(x7, s1)));
 }
-// cosine series (odd n); sg = -1 selects the negated-coefficient table
-__device__ __forceinline__ float sc_cos_poly(double x2, double sg) {
+// cosine series (odd n), positive-coefficient table
+__device__ __forceinline__ float sc_cos_poly(double x2) {
   double x4 = __dmul_rn(x2, x2);
-  double c2 = __dadd_rn(sg * RL_SC_C3, __dmul_rn(x2, sg * RL_SC_C4));
-  double c1 = __dadd_rn(sg * RL_SC_C0, __dmul_rn(x2, sg * RL_SC_C1));
+  double c2 = __dadd_rn(RL_SC_C3, __dmul_rn(x2, RL_SC_C4));
+  double c1 = __dadd_rn(RL_SC_C0, __dmul_rn(x2, RL_SC_C1));
   double x6 = __dmul_rn(x4, x2);
-  double c = __dadd_rn(c1, __dmul_rn(x4, sg * RL_SC_C2));
+  double c = __dadd_rn(c1, __dmul_rn(x4, RL_SC_C2));
   return __double2float_rn(__dadd_rn(c, __dmul_rn(x6, c2)));
 }
 
@@ -66,30 +66,27 @@ __device__ __forceinline__ double sc_reduce_large(uint32_t xi, int* np) {
 }
 
 // sinf(y) and cosf(y) together: one argument reduction, two polynomials.
+//
+// Written without data-dependent branches for |y| < 120 (a warp of rays holds 32 unrelated headings):
+//  * the published |y| < pi/4 shortcut (abstop12 < 0x3f4, i.e. |y| < 0.75) is the general path with n = 0 --
+//    reduce_fast then returns x - 0 * hpi = x and the same two polynomials run on it;
+//  * the published sign handling multiplies the argument of the odd polynomial by sign[n & 3] and switches to
+//    a table of negated coefficients for n & 2; every operation in both polynomials is odd / linear in that
+//    sign and round-to-nearest is symmetric, so negating the float results is bit-identical and saves the
+//    multiplications.
 __device__ __forceinline__ void rl_sincosf(float y, float* sp, float* cp) {
-  uint32_t bits = __float_as_uint(y);
-  uint32_t top = (bits >> 20) & 0x7ff;
+  const uint32_t bits = __float_as_uint(y);
+  const uint32_t top = (bits >> 20) & 0x7ff;
   double x = (double)y;
-  if (top < 0x3f4u) {  // |y| < ~pi/4 (abstop12 compare, as published)
-    double x2 = __dmul_rn(x, x);
-    if (top < 0x398u) {  // |y| < 2^-12
-      *sp = y;
-      *cp = 1.0f;
-      return;
-    }
-    *sp = sc_sin_poly(x, x2);
-    *cp = sc_cos_poly(x2, 1.0);
-    return;
-  }
   int n;
-  int q;  // quadrant index that selects sign and table
+  int q;  // quadrant index that selects the signs
   if (top < 0x42fu) {  // |y| < 120
-    double r = __dmul_rn(x, RL_SC_HPI_INV);
+    const double r = __dmul_rn(x, RL_SC_HPI_INV);
     n = (__double2int_rz(r) + 0x800000) >> 24;
     x = __dsub_rn(x, __dmul_rn((double)n, RL_SC_HPI));
     q = n;
   } else if (top < 0x7f8u) {
-    int sign = bits >> 31;
+    const int sign = bits >> 31;
     x = sc_reduce_large(bits, &n);
     q = n + sign;
   } else {  // inf / nan
@@ -97,20 +94,19 @@ __device__ __forceinline__ void rl_sincosf(float y, float* sp, float* cp) {
     *cp = *sp;
     return;
   }
-  double s = ((q & 3) == 1 || (q & 3) == 2) ? -1.0 : 1.0;  // sign[] = {1,-1,-1,1}
-  double sg = (q & 2) ? -1.0 : 1.0;
-  double xs = __dmul_rn(x, s);
-  double x2 = __dmul_rn(x, x);
-  // sin uses poly index n, cos uses n^1
-  float a = sc_sin_poly(xs, x2);   // even-index polynomial
-  float b = sc_cos_poly(x2, sg);   // odd-index polynomial
-  if ((n & 1) == 0) {
-    *sp = a;
-    *cp = b;
-  } else {
-    *sp = b;
-    *cp = a;
+  const double x2 = __dmul_rn(x, x);
+  float a = sc_sin_poly(x, x2);  // even-index polynomial, argument sign[q & 3] = {1,-1,-1,1}
+  float b = sc_cos_poly(x2);     // odd-index polynomial, negated table for q & 2
+  a = (((q + 1) & 2) != 0) ? -a : a;
+  b = ((q & 2) != 0) ? -b : b;
+  float sn = ((n & 1) == 0) ? a : b;  // sin uses polynomial n, cos uses n ^ 1
+  float cs = ((n & 1) == 0) ? b : a;
+  if (top < 0x398u) {  // |y| < 2^-12: sinf returns y, cosf returns 1
+    sn = y;
+    cs = 1.0f;
   }
+  *sp = sn;
+  *cp = cs;
 }
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }

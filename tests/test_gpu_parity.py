@@ -212,9 +212,11 @@ def test_dynamic_map_update_rm_and_cddt():
     assert_bit_equal(out, port.Oracle(port.PCDDT, occ, MR, TD, threads=8).calc_range_many(q), "pcddt after update")
 
 
-@pytest.mark.parametrize("variant", [1])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_rm_persistent_kernel_large_batches(variant):
-    """Batches large enough for the persistent-warp / lane re-queuing kernel, all three entry points."""
+    """Batches large enough for the persistent-warp / lane re-queuing kernel, all three entry points.
+    Variants: 1 default (parked rays in registers), 2 conditional load, 3 parked rays in shared memory,
+    4 two rays per lane -- performance knobs, identical results."""
     occ = wl.load_map("basement_hallways_5cm")
     W, H = occ.shape
     world = (0.05, 0.0, -30.0, -30.0, 0.0, 1.0)
