@@ -18,6 +18,8 @@
 // KIND: RL_BL (:696-769), RL_RM (:927-962), RL_CDDT / RL_PCDDT (:1342-1516), RL_GLT (:1869-1880).
 #include <cstdlib>
 
+#include <type_traits>
+
 #include "rl_internal.cuh"
 #include "rl_math.cuh"
 
@@ -615,12 +617,23 @@ radial_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const flo
 // One CTA handles `ppb` consecutive particles per iteration (grid-stride over particle groups).
 // Beams are processed in chunks of at most `chunk` so shared memory stays bounded for any M.
 // smem: double vals[ppb * chunk].
-template <int KIND>
+// PARAM_BEAMS: angles and observation arrive as kernel parameters (rl::BeamParams) and are staged in shared memory.
+template <int KIND, bool PARAM_BEAMS>
 __global__ void __launch_bounds__(256, KIND == RL_RM ? 7 : 4)
 fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_range, const float* __restrict__ ins,
              const float* __restrict__ angles, const float* __restrict__ obs, double* __restrict__ weights, int N,
-             int M, int ppb, int chunk, PeerOut peers) {
+             int M, int ppb, int chunk, PeerOut peers,
+             typename std::conditional<PARAM_BEAMS, BeamParams, NoBeamParams>::type beams) {
   extern __shared__ double vals[];
+  __shared__ float s_beams[PARAM_BEAMS ? 2 * RL_PARAM_BEAMS : 1];
+  if (PARAM_BEAMS) {
+    const BeamParams& bp = reinterpret_cast<const BeamParams&>(beams);
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+      s_beams[i] = bp.angles[i];
+      s_beams[RL_PARAM_BEAMS + i] = bp.obs[i];
+    }
+    __syncthreads();
+  }
   const float kmax = (float)((double)(float)sv.K - 1.0);
   const int groups = (N + ppb - 1) / ppb;
   long long epoch = 0;
@@ -655,7 +668,7 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
           world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
           gx = y;
           gy = x;
-          gth = fsub(th, __ldg(angles + a));
+          gth = fsub(th, PARAM_BEAMS ? s_beams[a] : __ldg(angles + a));
         }
         float d;
         if (KIND == RL_RM) {
@@ -667,7 +680,8 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
         }
         if (valid) {
           const int di = sensor_index(d, kmax);                                   // :602-603 (no scaling)
-          const int ri = sensor_index(fmul(__ldg(obs + a), xf.inv_scale), kmax);  // :605-606
+          const float ob = PARAM_BEAMS ? s_beams[RL_PARAM_BEAMS + a] : __ldg(obs + a);
+          const int ri = sensor_index(fmul(ob, xf.inv_scale), kmax);  // :605-606
           vals[p * cm + (a - c0)] = __ldg(sv.table + (size_t)ri * sv.K + di);
         }
       }
@@ -1035,8 +1049,8 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     const size_t smem = (size_t)ppb * chunk * sizeof(double);
     PeerOut po{};
     if (peers) po = *peers;
-    fused_kernel<KIND><<<grid, threads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range, ins, angles,
-                                                           obs, weights, n, M, ppb, chunk, po);
+    fused_kernel<KIND, false><<<grid, threads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range, ins,
+                                                                  angles, obs, weights, n, M, ppb, chunk, po, NoBeamParams{});
   } else {
     const long long total = (mode == MODE_ANGLES) ? (long long)n * M : (long long)n;
     // RM with enough rays to give every resident warp more than one ray per lane: persistent
@@ -1110,6 +1124,39 @@ int launch_cast(rl_method* m, int mode, const float* ins, const float* angles, c
     case RL_RM: return launch_cast_kind<RL_RM>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
     case RL_GLT: return launch_cast_kind<RL_GLT>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
     default: return launch_cast_kind<RL_CDDT>(m, mode, ins, angles, obs, outs, weights, n, M, peers);
+  }
+}
+
+template <int KIND>
+static int launch_fused_beam_params_kind(rl_method* m, const float* ins, const BeamParams& beams, double* weights, int n,
+                                         int M) {
+  MapView mv = m->map_view();
+  const int threads = 256;
+  if ((long long)n * M > 2LL * sm_count() * 7 * threads) mv.coop_threshold = 0;  // as in launch_cast_kind
+  const int chunk = min(M, 2048);
+  const int ppb = max(1, min(threads / max(M, 1), 32));
+  const int groups = (n + ppb - 1) / ppb;
+  const int grid = max(1, min(groups, sm_count() * 8));
+  const size_t smem = (size_t)ppb * chunk * sizeof(double);
+  fused_kernel<KIND, true><<<grid, threads, smem, m->stream>>>(mv, m->cddt_view(), m->xf, m->sensor_view(), m->max_range,
+                                                               ins, nullptr, nullptr, weights, n, M, ppb, chunk,
+                                                               PeerOut{}, beams);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
+}
+
+// the fused call with angles / observation passed inside the launch; n, M > 0, M <= RL_PARAM_BEAMS
+int launch_fused_beam_params(rl_method* m, const float* ins, const BeamParams& beams, double* weights, int n, int M) {
+  if (!m->d_table) {
+    set_error("calc_range_repeat_angles_eval_sensor_model: set_sensor_model has not been called");
+    return RL_E_STATE;
+  }
+  switch (m->kind) {
+    case RL_BL: return launch_fused_beam_params_kind<RL_BL>(m, ins, beams, weights, n, M);
+    case RL_RM: return launch_fused_beam_params_kind<RL_RM>(m, ins, beams, weights, n, M);
+    case RL_GLT: return launch_fused_beam_params_kind<RL_GLT>(m, ins, beams, weights, n, M);
+    default: return launch_fused_beam_params_kind<RL_CDDT>(m, ins, beams, weights, n, M);
   }
 }
 

@@ -108,6 +108,15 @@ struct PeerOut {
   unsigned* counter;               // local: CTAs finished in the current launch
 };
 
+// Small fused calls through HOST pointers carry the beam angles and the observation inside the launch (kernel
+// parameters) instead of a host-to-device copy.
+#define RL_PARAM_BEAMS 256
+struct BeamParams {
+  float angles[RL_PARAM_BEAMS];
+  float obs[RL_PARAM_BEAMS];
+};
+struct NoBeamParams {};
+
 }  // namespace rl
 
 struct rl_map {
@@ -202,6 +211,8 @@ void cddt_free(rl_method* m);
 // rl_cast.cu -- the batched query kernels (all kinds, all modes)
 int launch_cast(rl_method* m, int mode, const float* d_ins, const float* d_angles, const float* d_obs, float* d_outs,
                 double* d_weights, int n, int num_angles, const PeerOut* peers = nullptr);
+int launch_fused_beam_params(rl_method* m, const float* d_ins, const BeamParams& beams, double* d_weights, int n,
+                             int num_angles);
 int launch_radial(rl_method* m, const float* d_ins, const float* d_beam_angles, float* d_outs, int n, int num_rays,
                   int count, int max_pair, int index_offset);
 int launch_eval_sensor(rl_method* m, const float* d_obs, const float* d_ranges, double* d_outs, int m_rays, int n);

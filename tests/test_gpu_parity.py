@@ -581,3 +581,32 @@ def test_device_map_ingest_rgba_and_occupancy_grid():
         assert_bit_equal(a, b, "PCDDT ranges after occupancy-grid ingest")
     with pytest.raises(rl.RangeLibError):
         cd.set_map_occupancy_grid(data[:-1])
+
+
+@pytest.mark.parametrize("kn", ["rm", "bl", "pcddt"])
+def test_fused_small_host_call_paths(kn):
+    """The small host-pointer fused call (poses by one async copy straight from pinned caller memory, angles and
+    observation inside the launch, weights stored into pinned host memory) against the oracle, for pinned and
+    pageable caller arrays, beam counts on both sides of the in-launch limit (256), and a sub-array view."""
+    import torch
+    occ = wl.load_map("basement_hallways_10cm")
+    world = (0.1, 0.0, -5.0, 3.0, 0.0, 1.0)
+    meth = make(kn, occ, world=world)
+    table = wl.sensor_table(501)
+    meth.set_sensor_model(table)
+    o = port.Oracle(KINDS[kn], occ, MR, TD, threads=8)
+    o.set_world(*world)
+    o.set_sensor_model(table)
+    rng = np.random.default_rng(4)
+    for n, m_beams in ((1, 1), (777, 60), (4000, 60), (50, 256), (50, 257), (9, 1080)):
+        parts = wl.grid_to_world(wl.pf_particles_uniform(occ, n, seed=n), world[0], world[2], world[3])
+        angles = wl.lidar_angles(m_beams) if m_beams > 1 else np.zeros(1, np.float32)
+        obs = rng.uniform(0, 50.0, m_beams).astype(np.float32)
+        want = o.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs)
+        for pin in (False, True):
+            mk = (lambda a: torch.from_numpy(a.copy()).pin_memory().numpy()) if pin else (lambda a: a.copy())
+            hp, ha, ho = mk(parts), mk(angles), mk(obs)
+            hw = mk(np.full(n + 3, -1.0))
+            meth.calc_range_repeat_angles_eval_sensor_model(hp, ha, ho, hw[1:n + 1])  # view with an offset
+            assert_bit_equal(hw[1:n + 1], want, "%s n=%d m=%d pinned=%s" % (kn, n, m_beams, pin))
+            assert hw[0] == -1.0 and (hw[n + 1:] == -1.0).all()
