@@ -321,6 +321,7 @@ static void free_method(rl_method* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   cddt_free(m);
+  sort_free(m);
   cudaFree(m->d_occ);
   cudaFree(m->d_bits_t);
   cudaFree(m->d_dt);

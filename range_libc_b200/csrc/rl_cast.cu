@@ -623,7 +623,8 @@ __global__ void __launch_bounds__(256, KIND == RL_RM ? 7 : 4)
 fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_range, const float* __restrict__ ins,
              const float* __restrict__ angles, const float* __restrict__ obs, double* __restrict__ weights, int N,
              int M, int ppb, int chunk, PeerOut peers,
-             typename std::conditional<PARAM_BEAMS, BeamParams, NoBeamParams>::type beams) {
+             typename std::conditional<PARAM_BEAMS, BeamParams, NoBeamParams>::type beams,
+             const int* __restrict__ perm) {
   extern __shared__ double vals[];
   __shared__ float s_beams[PARAM_BEAMS ? 2 * RL_PARAM_BEAMS : 1];
   if (PARAM_BEAMS) {
@@ -663,7 +664,7 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
         if (valid) {
           p = k / cm;
           a = c0 + (k - p * cm);
-          const int i = p0 + p;
+          const size_t i = perm ? (size_t)__ldg(perm + p0 + p) : (size_t)(p0 + p);  // processing order only
           float x, y, th;
           world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
           gx = y;
@@ -693,10 +694,11 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
       __syncthreads();
     }
     if (threadIdx.x < np) {
+      const size_t i = perm ? (size_t)__ldg(perm + p0 + threadIdx.x) : (size_t)(p0 + threadIdx.x);
       if (peers.n == 0) {
-        weights[p0 + threadIdx.x] = w;
+        weights[i] = w;
       } else {  // all-gather by direct peer stores (NVLink): every GPU gets this rank's slice
-        for (int r = 0; r < peers.n; ++r) out_ptrs[r][peers.offset + p0 + threadIdx.x] = w;
+        for (int r = 0; r < peers.n; ++r) out_ptrs[r][peers.offset + i] = w;
       }
     }
   }
@@ -839,6 +841,9 @@ bl_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
 // batches and the marching loop runs with most lanes busy until the chunk is exhausted.
 // ------------------------------------------------------------------------------------------
 #define RL_QB 4  // parked rays per lane and setup phase
+#ifndef RL_FUSED_GROUP_RAYS
+#define RL_FUSED_GROUP_RAYS 4096  // rays of one particle group in fused_rm_persist_kernel (2048: -8 %, 6144: -30 %)
+#endif
 #ifndef RL_RM_BURST_PAIRS
 #define RL_RM_BURST_PAIRS 3  // sphere-tracing steps per refill round = 2 * this
 #endif
@@ -1010,6 +1015,129 @@ rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused RM sensor update for launches many waves deep (a global-localisation cloud, BASELINE config 5).
+// fused_kernel marches one ray per thread to completion, which is what a launch that fits the chip once wants
+// (with its cooperative tail); deep launches are throughput problems and get the marching loop of
+// rm_persist_kernel instead: a CTA takes a group of particles whose rays (<= 2048) it numbers 0..R-1; its warps
+// draw batches of 32 rays from a shared counter, set them up convergently, park them in registers, and every
+// lane whose ray has ended takes the next parked one.  A finished ray goes straight through the sensor table
+// into shared memory; when the group's rays are done one thread per particle forms the product in beam order
+// (bit-identical to the reference's sequential product).  Ranges never reach HBM.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 5)
+fused_rm_persist_kernel(MapView mv, WorldXform xf, SensorView sv, float max_range, const float* __restrict__ ins,
+                        const float* __restrict__ angles, const float* __restrict__ obs,
+                        double* __restrict__ weights, int N, int M, int ppb, int chunk, PeerOut peers,
+                        const int* __restrict__ perm, int burst_pairs) {
+  extern __shared__ double vals[];
+  __shared__ int s_next;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const float kmax = (float)((double)(float)sv.K - 1.0);
+  const float* __restrict__ dt = mv.dt;
+  const unsigned W = (unsigned)mv.W, H = (unsigned)mv.H;
+  const int groups = (N + ppb - 1) / ppb;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int p0 = g * ppb;
+    const int np = min(ppb, N - p0);
+    double w = 1.0;  // running product, owned by thread p < np
+    for (int c0 = 0; c0 < M; c0 += chunk) {
+      const int cm = min(chunk, M - c0);
+      const int rays = np * cm;
+      if (threadIdx.x == 0) s_next = 0;
+      __syncthreads();
+      // ---- this warp's share of the group's rays: lane re-queuing as in rm_persist_kernel ----
+      RmSlot r;
+      r.x0 = r.y0 = r.dx = r.dy = r.t = 0.f;
+      r.id = 0;
+      r.busy = r.alive = false;
+      float4 parked = make_float4(0.f, 0.f, 0.f, 0.f);
+      int batch_base = 0, batch_n = 0, batch_pos = 0;
+      bool more = true;
+      while (true) {
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const unsigned idle = __ballot_sync(FULL, !r.busy);
+          if (idle) {
+            if (batch_pos == batch_n && more) {
+              int b = 0;
+              if (lane == 0) b = atomicAdd(&s_next, 32);
+              b = __shfl_sync(FULL, b, 0);
+              batch_pos = 0;
+              if (b >= rays) {
+                more = false;
+                batch_n = 0;
+              } else {
+                batch_base = b;
+                batch_n = min(32, rays - b);
+                if (lane < batch_n) {
+                  const int k = b + lane;
+                  const int p = k / cm;
+                  const int a = c0 + (k - p * cm);
+                  const size_t i = perm ? (size_t)__ldg(perm + p0 + p) : (size_t)(p0 + p);
+                  float x, y, th;
+                  world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
+                  const float gth = fsub(th, __ldg(angles + a));
+                  float sn = 0.f, cs = 0.f;
+                  const bool ok = finite3(y, x, gth);
+                  if (ok) rl_sincosf(gth, &sn, &cs);
+                  // calc_range(y, x, theta) RangeLib.h:594; a non-finite pose leaves the map at once -> max_range
+                  parked = ok ? make_float4(y, x, cs, sn) : make_float4(-1e30f, 0.f, 0.f, 0.f);
+                }
+              }
+            }
+            const int avail = batch_n - batch_pos;
+            if (avail > 0) {
+              const int rank = __popc(idle & ((1u << lane) - 1u));
+              const bool take = !r.busy && rank < avail;
+              const int src = (batch_pos + rank) & 31;
+              const float px = __shfl_sync(FULL, parked.x, src), py = __shfl_sync(FULL, parked.y, src);
+              const float pz = __shfl_sync(FULL, parked.z, src), pw = __shfl_sync(FULL, parked.w, src);
+              if (take) {
+                r.x0 = px; r.y0 = py; r.dx = pz; r.dy = pw;
+                r.t = 0.0f;
+                r.id = batch_base + batch_pos + rank;
+                r.busy = r.alive = true;
+              }
+              batch_pos += min(avail, __popc(idle));
+            }
+          }
+        }
+        if (!__any_sync(FULL, r.busy)) break;
+#pragma unroll 1
+        for (int b = 0; b < burst_pairs; ++b) {
+          rm_step_pred<false>(dt, W, H, max_range, r);
+          rm_step_pred<false>(dt, W, H, max_range, r);
+        }
+        if (r.busy && !r.alive) {
+          const float d = rm_result(W, H, max_range, r);
+          const int k = r.id;
+          const int a = c0 + (k - (k / cm) * cm);
+          const int di = sensor_index(d, kmax);                                   // :602-603 (no scaling)
+          const int ri = sensor_index(fmul(__ldg(obs + a), xf.inv_scale), kmax);  // :605-606
+          vals[k] = __ldg(sv.table + (size_t)ri * sv.K + di);
+          r.busy = false;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < np) {
+        const double* v = vals + threadIdx.x * cm;
+        for (int a = 0; a < cm; ++a) w = __dmul_rn(w, v[a]);  // reference order: beam ascending
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < np) {
+      const size_t i = perm ? (size_t)__ldg(perm + p0 + threadIdx.x) : (size_t)(p0 + threadIdx.x);
+      if (peers.n == 0) {
+        weights[i] = w;
+      } else {  // all-gather by direct peer stores (NVLink): every GPU gets this rank's slice
+        for (int rr = 0; rr < peers.n; ++rr) peers.ptr[rr][peers.offset + i] = w;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
 static int g_sm_count = 0;
@@ -1049,8 +1177,34 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     const size_t smem = (size_t)ppb * chunk * sizeof(double);
     PeerOut po{};
     if (peers) po = *peers;
-    fused_kernel<KIND, false><<<grid, threads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range, ins,
-                                                                  angles, obs, weights, n, M, ppb, chunk, po, NoBeamParams{});
+    // big clouds on structures larger than L2: process the particles tile by tile (rl_sort.cu)
+    static const bool spatial = !(getenv("RL_SPATIAL_SORT") && atoi(getenv("RL_SPATIAL_SORT")) == 0);
+    const int* perm = nullptr;
+    const size_t struct_bytes = (KIND == RL_RM) ? m->dt_elems() * sizeof(float)
+                                : (KIND == RL_GLT) ? m->dt_elems() * (size_t)m->td * sizeof(uint16_t) : 0;
+    if (spatial && n >= 32768 && struct_bytes > ((size_t)48 << 20)) {
+      const int rc = spatial_order(m, ins, n, &perm);
+      if (rc) return rc;
+    }
+    static const bool deep = !(getenv("RL_FUSED_PERSIST") && atoi(getenv("RL_FUSED_PERSIST")) == 0);
+    static const int group_rays = getenv("RL_FUSED_GROUP_RAYS") ? atoi(getenv("RL_FUSED_GROUP_RAYS")) : RL_FUSED_GROUP_RAYS;
+    // many waves deep and at least six particles per group: the re-queuing kernel (measured, basement 5 cm map:
+    // 100000 x 60 16.8 -> 25.0 G rays/s, 50000 x 360 22.2 -> 30.2; 8192^2 map, 10^6 x 60 14.2 -> 22.0).  With few
+    // ~1000-beam particles per group the neighbouring beams of fused_kernel's warps already finish together and
+    // the per-group tail of the re-queuing loop costs more than it saves (20000 x 1080: 33.9 vs 30.0).
+    if (KIND == RL_RM && deep && mv.coop_threshold == 0 && m->max_range > 0.0f && !po.sig && m->persist &&
+        6 * M <= group_rays) {
+      const int ppb2 = max(1, min(group_rays / max(M, 1), 128));
+      const int groups2 = (n + ppb2 - 1) / ppb2;
+      const int grid2 = max(1, min(groups2, sm_count() * 5));
+      fused_rm_persist_kernel<<<grid2, 256, (size_t)ppb2 * chunk * sizeof(double), m->stream>>>(
+          mv, m->xf, m->sensor_view(), m->max_range, ins, angles, obs, weights, n, M, ppb2, chunk, po, perm,
+          RL_RM_BURST_PAIRS);
+    } else {
+      fused_kernel<KIND, false><<<grid, threads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range, ins,
+                                                                    angles, obs, weights, n, M, ppb, chunk, po,
+                                                                    NoBeamParams{}, perm);
+    }
   } else {
     const long long total = (mode == MODE_ANGLES) ? (long long)n * M : (long long)n;
     // RM with enough rays to give every resident warp more than one ray per lane: persistent
@@ -1140,7 +1294,7 @@ static int launch_fused_beam_params_kind(rl_method* m, const float* ins, const B
   const size_t smem = (size_t)ppb * chunk * sizeof(double);
   fused_kernel<KIND, true><<<grid, threads, smem, m->stream>>>(mv, m->cddt_view(), m->xf, m->sensor_view(), m->max_range,
                                                                ins, nullptr, nullptr, weights, n, M, ppb, chunk,
-                                                               PeerOut{}, beams);
+                                                               PeerOut{}, beams, nullptr);
   count_launch();
   RL_CHECK_LAUNCH();
   return RL_OK;

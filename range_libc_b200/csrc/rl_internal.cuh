@@ -169,6 +169,12 @@ struct rl_method {
   void* h_stage = nullptr;      // pinned + mapped
   void* h_stage_dev = nullptr;  // its device alias (zero-copy)
   size_t h_stage_bytes = 0;
+  // spatial ordering of large particle sets (rl_sort.cu)
+  unsigned* d_sort_keys = nullptr;
+  int* d_sort_idx = nullptr;
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  int sort_cap = 0;
   // calc_range_many_radial_optimized: beam-angle table of the last call
   float* d_radial = nullptr;
   int radial_cap = 0, radial_rays = -1, radial_count = 0;
@@ -208,6 +214,9 @@ int apply_patch_batch(rl_method* m, const uint8_t* d_patches, const int* d_rects
 int cddt_build(rl_method* m);
 int cddt_prune(rl_method* m, float max_range);
 void cddt_free(rl_method* m);
+// rl_sort.cu
+int spatial_order(rl_method* m, const float* d_ins, int n, const int** d_perm);
+void sort_free(rl_method* m);
 // rl_cast.cu -- the batched query kernels (all kinds, all modes)
 int launch_cast(rl_method* m, int mode, const float* d_ins, const float* d_angles, const float* d_obs, float* d_outs,
                 double* d_weights, int n, int num_angles, const PeerOut* peers = nullptr);

@@ -610,3 +610,57 @@ def test_fused_small_host_call_paths(kn):
             meth.calc_range_repeat_angles_eval_sensor_model(hp, ha, ho, hw[1:n + 1])  # view with an offset
             assert_bit_equal(hw[1:n + 1], want, "%s n=%d m=%d pinned=%s" % (kn, n, m_beams, pin))
             assert hw[0] == -1.0 and (hw[n + 1:] == -1.0).all()
+
+
+def test_large_cloud_spatial_ordering_is_invisible():
+    """Big clouds on a map whose distance transform exceeds the L2 threshold are processed tile by tile
+    (rl_sort.cu); weights land at their own indices and equal the oracle's bit for bit."""
+    import torch
+    occ = wl.synthetic_map(4096, seed=5)  # 64 MB distance transform
+    meth = make("rm", occ)
+    table = wl.sensor_table(501)
+    meth.set_sensor_model(table)
+    n, m_beams = 40000, 6
+    parts = wl.pf_particles_uniform(occ, n, seed=12)
+    parts[7] = [np.nan, 1.0, 0.0]        # non-finite and out-of-map poses go through the key kernel too
+    parts[8] = [-1e9, 5e9, 1.0]
+    angles = wl.lidar_angles(m_beams)
+    obs = np.linspace(20.0, 400.0, m_beams).astype(np.float32)
+    o = port.Oracle(port.RM, occ, MR, threads=8)
+    o.set_sensor_model(table)
+    want = o.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs)
+    got = torch.empty(n, dtype=torch.float64, device="cuda")
+    l0 = rl.kernel_launches()
+    meth.calc_range_repeat_angles_eval_sensor_model(torch.from_numpy(parts).cuda(), torch.from_numpy(angles).cuda(),
+                                                    torch.from_numpy(obs).cuda(), got)
+    meth.synchronize()
+    assert rl.kernel_launches() - l0 >= 3, "the ordering pass did not run"
+    assert_bit_equal(got.cpu().numpy(), want, "spatially ordered fused update")
+
+
+@pytest.mark.parametrize("n,m_beams", [(12000, 60), (700, 1080), (300, 2500), (600011, 1)])
+def test_deep_fused_launches_use_requeuing_kernel(n, m_beams):
+    """Fused RM updates many waves deep run on fused_rm_persist_kernel (lane re-queuing inside a CTA's particle
+    group, product in beam order): weights bit-equal to the oracle, rotated world frame, odd sizes."""
+    import torch
+    occ = wl.load_map("basement_hallways_5cm")
+    world = (0.05, 0.3, -3.0, 2.0, float(np.float32(np.sin(0.3))), float(np.float32(np.cos(0.3))))
+    meth = make("rm", occ, world=world)
+    table = wl.sensor_table(501)
+    meth.set_sensor_model(table)
+    o = port.Oracle(port.RM, occ, MR, threads=8)
+    o.set_world(*world)
+    o.set_sensor_model(table)
+    parts = wl.grid_to_world(wl.pf_particles_uniform(occ, n, seed=n), world[0], world[2], world[3], world[1])
+    parts[n // 2] = [np.inf, 0.0, 0.0]
+    angles = wl.lidar_angles(m_beams) if m_beams > 1 else np.array([0.1], np.float32)
+    obs = np.random.default_rng(9).uniform(0, 25.0, m_beams).astype(np.float32)
+    want = o.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs)
+    got = np.empty(n, np.float64)
+    meth.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs, got)
+    assert_bit_equal(got, want, "deep fused %dx%d (host)" % (n, m_beams))
+    d_got = torch.empty(n, dtype=torch.float64, device="cuda")
+    meth.calc_range_repeat_angles_eval_sensor_model(torch.from_numpy(parts).cuda(), torch.from_numpy(angles).cuda(),
+                                                    torch.from_numpy(obs).cuda(), d_got)
+    meth.synchronize()
+    assert_bit_equal(d_got.cpu().numpy(), want, "deep fused %dx%d (device)" % (n, m_beams))
