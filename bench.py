@@ -491,6 +491,15 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "fused_kernel<RM>", "algorithmic_bytes_per_launch": algo_bytes,
                      "peak_source": peak_src, "l2_sector_bytes_per_launch": l2_bytes,
+                     "l2_gather": None if not l2_bytes else {
+                         "achieved_gsectors_per_s": l2_bytes / 32.0 / (kernel_ms * 1e-3) / 1e9,
+                         "peak_gsectors_per_s": 291.0,
+                         "frac": l2_bytes / 32.0 / (kernel_ms * 1e-3) / 291e9,
+                         "what": "32-byte sectors through L2 per launch (ncu lts__t_sectors, committed capture) over the "
+                                 "measured kernel time, against the chip's random-gather rate: one L1-miss request per "
+                                 "clock per SM = 148 x 1.965 GHz, which tools/gather_bench.cu reproduces (287-292 G/s). "
+                                 "The large-batch RM kernel runs at ~90 % of it (profiles/ncu_cast_r01.txt); this 240k-ray "
+                                 "launch fits the chip once and is bound by launch + set-up + its longest dependent chain"},
                      "note": "0.335 algorithmic B/ray: this path is bound by the latency of the longest sphere-tracing "
                              "chain in the launch (dependent L2 reads, ~143 ns each on B200) and by L2 sector traffic, not by "
                              "HBM (DESIGN.md section 4); traffic = DRAM bytes per launch from the committed ncu capture "
