@@ -664,3 +664,48 @@ def test_deep_fused_launches_use_requeuing_kernel(n, m_beams):
                                                     torch.from_numpy(obs).cuda(), d_got)
     meth.synchronize()
     assert_bit_equal(d_got.cpu().numpy(), want, "deep fused %dx%d (device)" % (n, m_beams))
+
+
+def test_fuzz_small_random_maps_all_kinds():
+    """Random small non-square maps x {BL, RM, CDDT, PCDDT} x odd theta discretizations / max ranges / world
+    frames: grid, world, angle-fan and fused entry points against the oracle (itself fuzzed against the
+    unmodified reference in tests/test_oracle_vs_ref.py), queries inside and outside the map."""
+    rng = np.random.default_rng(20261018)
+    for it in range(24):
+        W, H = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        occ = (rng.random((W, H)) < rng.choice([0.0, 0.02, 0.1, 0.3])).astype(np.uint8)
+        if rng.random() < 0.5:
+            occ[int(rng.integers(0, W)), :] = 1
+        mr = float(rng.choice([3.5, 20.0, 50.0, 500.0]))
+        td = int(rng.choice([4, 7, 16, 108, 361]))
+        ang = float(rng.uniform(-3, 3))
+        world = (float(rng.choice([1.0, 0.05, 2.5])), ang, float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5)),
+                 float(np.float32(np.sin(ang))), float(np.float32(np.cos(ang))))
+        q = wl.random_queries(max(W, 2), max(H, 2), 300, seed=it)
+        q[:40, :2] += rng.uniform(-8, 8, (40, 2)).astype(np.float32)  # some start outside the map
+        qw = wl.grid_to_world(q, world[0], world[2], world[3], world[1])
+        parts = qw[:50]
+        angles = wl.lidar_angles(int(rng.integers(1, 40)) + 1)
+        obs = rng.uniform(0, mr * world[0], len(angles)).astype(np.float32)
+        K = int(rng.integers(2, 60))
+        table = rng.uniform(0.05, 1.0, (K, K))
+        for kn in ("bl", "rm", "cddt", "pcddt"):
+            what = "iter %d %s map %dx%d mr %g td %d" % (it, kn, W, H, mr, td)
+            meth = make(kn, occ, max_range=mr, td=td, world=world)
+            o = port.Oracle(KINDS[kn], occ, mr, td)
+            o.set_world(*world)
+            out = np.empty(len(q), np.float32)
+            meth.calc_range_many_grid(q, out)
+            assert_bit_equal(out, o.calc_range_many(q), what + " grid")
+            meth.calc_range_many(qw, out)
+            assert_bit_equal(out, o.numpy_calc_range(qw), what + " world")
+            fan = np.empty(len(parts) * len(angles), np.float32)
+            meth.calc_range_repeat_angles(parts, angles, fan)
+            assert_bit_equal(fan, o.numpy_calc_range_angles(parts, angles), what + " angles")
+            meth.set_sensor_model(table)
+            o.set_sensor_model(table)
+            w = np.empty(len(parts), np.float64)
+            meth.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs, w)
+            assert_bit_equal(w, o.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs), what + " fused")
+            meth.eval_sensor_model(obs, fan, w, len(angles), len(parts))
+            assert_bit_equal(w, o.eval_sensor_model(obs, fan, len(angles), len(parts)), what + " two-step")

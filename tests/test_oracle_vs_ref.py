@@ -88,3 +88,38 @@ def test_noise_floor_against_the_shipped_flag_build():
     print("STRICT vs SHIPPED (bit-mismatch, >1e-4 rel, >1 px):", report)
     assert report["rm"][1] < 1e-4 and report["bl"][1] < 1e-4 and report["cddt"][1] < 2e-3
     assert all(v[2] < 1e-4 for v in report.values())
+
+
+def _random_small_map(rng):
+    W, H = int(rng.integers(3, 70)), int(rng.integers(3, 70))
+    occ = (rng.random((W, H)) < rng.choice([0.02, 0.1, 0.3])).astype(np.uint8)
+    if rng.random() < 0.5:  # a wall or two
+        occ[int(rng.integers(0, W)), :] = 1
+        occ[:, int(rng.integers(0, H))] = 1
+    return occ
+
+
+def test_fuzz_small_random_maps_rm_cddt():
+    """Random small non-square maps, odd theta discretizations and max ranges: the restatement against the
+    unmodified reference for RM / CDDT / PCDDT (queries inside the map -- outside it the reference's CDDT indexes
+    its grid out of bounds, RangeLib.h:1413), plus distance transform and tables."""
+    rng = np.random.default_rng(20261017)
+    for it in range(40):
+        occ = _random_small_map(rng)
+        W, H = occ.shape
+        mr = float(rng.choice([3.5, 20.0, 50.0, 500.0]))
+        td = int(rng.choice([4, 7, 16, 108, 361]))
+        q = wl.random_queries(W, H, 400, seed=it)
+        q[:, 0] = np.clip(q[:, 0], 0.01, W - 1.01)
+        q[:, 1] = np.clip(q[:, 1], 0.01, H - 1.01)
+        q[:8, 2] = [0, np.pi / 2, np.pi, -np.pi, 2 * np.pi, 7.5, -9.0, 1e-4]
+        for kind in (ref.RM, ref.CDDT, ref.PCDDT):
+            r = ref.RefMethod(kind, ref.RefMap(occ=occ), mr, td)
+            o = port.Oracle(kind, occ, mr, td)
+            what = "iter %d kind %d map %dx%d mr %g td %d" % (it, kind, W, H, mr, td)
+            assert_bit_equal(o.calc_range_many(q), r.calc_range_many(q), what)
+            if kind == ref.RM:
+                assert_bit_equal(o.dt(), r.dt(), what + " dt")
+            else:
+                for a, b in zip(o.cddt_table(), r.cddt_table(td)):
+                    assert_bit_equal(a, b, what + " table")
