@@ -126,18 +126,60 @@ __device__ __forceinline__ float rm_march_coop(const MapView& mv, float max_rang
   }
 }
 
+// ---- predicated form of the step (used by every marching loop that runs a converged warp) ----
+// A lane whose ray has ended keeps its t, which by construction reproduces the end condition (t >= max_range,
+// or the out-of-map / obstacle cell at (int)(x0 + dx t), (int)(y0 + dy t)), so a burst of steps is straight-line
+// code -- no branch, no reconvergence point -- and rm_result classifies the ray afterwards from t alone.
+struct RmSlot {
+  float x0, y0, dx, dy, t;
+  int id;
+  bool busy;   // the slot holds a ray (marching, or ended and not yet written out)
+  bool alive;  // ... and it is still marching
+};
+
+template <bool COND_LOAD>
+__device__ __forceinline__ void rm_step_pred(const float* __restrict__ dt, unsigned W, unsigned H, float max_range,
+                                             RmSlot& r) {
+  const int px = __float2int_rz(fadd(r.x0, fmul(r.dx, r.t)));
+  const int py = __float2int_rz(fadd(r.y0, fmul(r.dy, r.t)));
+  const bool go = r.alive && (unsigned)px < W && (unsigned)py < H;
+  // COND_LOAD: lanes that are not marching issue no load (ptxas makes it a BSSY / BRA / BSYNC triple, three
+  // more instructions per step); otherwise they read cell 0 and ignore it (one more 128-byte line in the
+  // request -- the gather rate of this kernel is bounded by L1 tag lookups, one line per clock per SM)
+  float d = 0.0f;
+  if (COND_LOAD) {
+    if (go) d = __ldg(dt + ((unsigned)px * H + (unsigned)py));
+  } else {
+    d = __ldg(dt + (go ? (unsigned)px * H + (unsigned)py : 0u));
+  }
+  const bool adv = go && !(d <= 0.0f);
+  const float tn = fadd(r.t, fmaxf(fmul(d, 0.999f), 1.0f));
+  r.t = adv ? tn : r.t;
+  r.alive = adv && (tn < max_range);
+}
+
+// result of a ray that ended with parameter t (see above); RangeLib.h:938-961
+__device__ __forceinline__ float rm_result(unsigned W, unsigned H, float max_range, const RmSlot& r) {
+  if (!(r.t < max_range)) return max_range;
+  const int px = __float2int_rz(fadd(r.x0, fmul(r.dx, r.t)));
+  const int py = __float2int_rz(fadd(r.y0, fmul(r.dy, r.t)));
+  if ((unsigned)px >= W || (unsigned)py >= H) return max_range;
+  const float xd = fsub((float)px, r.x0), yd = fsub((float)py, r.y0);
+  return __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
+}
+
 // Marches the rays held by the threads of one CTA (blockDim.x <= 256) to completion.  Must be called by
 // ALL threads of the CTA (it synchronises).
-//   phase 1  every thread steps its own ray (rm_step) in bursts of RL_BLOCK_BURST iterations; after each burst
+//   phase 1  every thread steps its own ray (rm_step_pred) in bursts of RL_BLOCK_BURST iterations; after each burst
 //            the CTA counts the rays still alive.  This finishes the bulk of the rays (mean ~6 steps) at one
 //            dependent L2 read per step and lane;
-//   phase 2  once at most mv.coop_threshold rays are left (default 16: two per warp) they are parked in shared
+//   phase 2  once at most mv.coop_threshold rays are left (default 8: one per warp; 4..16 measure the same, profiles/tune_r01_fused.log) they are parked in shared
 //            memory and the warps of the CTA take them one at a time and finish each with all 32 lanes
 //            (rm_march_coop).  The long crawls along walls -- the rays that decide the duration of a small
 //            launch -- thus run concurrently on different warps, each at the cooperative rate, instead of
 //            holding a nearly empty warp each.
 // mv.coop_threshold == 0 (or a map / range too large for the 16-bit cell keys) keeps everything in phase 1.
-#define RL_BLOCK_BURST 8
+#define RL_BLOCK_BURST 12
 __device__ __forceinline__ float rm_march_block(const MapView& mv, float max_range, bool active, float x0, float y0,
                                                 float dx, float dy) {
   __shared__ float4 s_ray[256];
@@ -147,36 +189,42 @@ __device__ __forceinline__ float rm_march_block(const MapView& mv, float max_ran
   __shared__ int s_n, s_next;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  float t = 0.0f, result = max_range;
+  const float* __restrict__ dt = mv.dt;
+  const unsigned W = (unsigned)mv.W, H = (unsigned)mv.H;
+  RmSlot r;
+  r.x0 = x0; r.y0 = y0; r.dx = dx; r.dy = dy;
+  r.t = 0.0f;
+  r.id = 0;
+  r.busy = r.alive = active;
   const int handoff = (mv.W < 32768 && mv.H < 32768 && max_range < 32768.0f) ? min(mv.coop_threshold, 256) : 0;
   if (handoff <= 0) {
-    if (active)
-      while (!rm_step(mv, max_range, x0, y0, dx, dy, t, result)) {
-      }
-    return result;
+    while (__any_sync(FULL, r.alive)) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rm_step_pred<false>(dt, W, H, max_range, r);
+    }
+    return active ? rm_result(W, H, max_range, r) : max_range;
   }
   if (threadIdx.x == 0) {
     s_n = 0;
     s_next = 0;
   }
-  for (int bursts = 1;; ++bursts) {
-    if (active) {
-      int n = RL_BLOCK_BURST;
-      bool done;
-      do {
-        done = rm_step(mv, max_range, x0, y0, dx, dy, t, result);
-      } while (!done && --n);
-      active = !done;
+  for (int steps = 2 * mv.block_burst_pairs;; steps += 2 * mv.block_burst_pairs) {
+    if (__any_sync(FULL, r.alive)) {
+#pragma unroll 1
+      for (int b = 0; b < mv.block_burst_pairs; ++b) {
+        rm_step_pred<false>(dt, W, H, max_range, r);
+        rm_step_pred<false>(dt, W, H, max_range, r);
+      }
     }
-    const int alive = __syncthreads_count(active);
-    if (alive == 0) return result;
+    const int alive = __syncthreads_count(r.alive);
+    if (alive == 0) return active ? rm_result(W, H, max_range, r) : max_range;
     // few rays left -- or, after 24 steps, a moderate number of rays that are evidently long ones
-    if (alive <= handoff || (bursts >= 3 && alive <= 4 * handoff)) break;
+    if (alive <= handoff || (steps >= 24 && alive <= 4 * handoff)) break;
   }
-  if (active) {
+  if (r.alive) {
     const int q = atomicAdd(&s_n, 1);
     s_ray[q] = make_float4(x0, y0, dx, dy);
-    s_t[q] = t;
+    s_t[q] = r.t;
     s_slot[q] = (short)threadIdx.x;
   }
   __syncthreads();
@@ -187,12 +235,12 @@ __device__ __forceinline__ float rm_march_block(const MapView& mv, float max_ran
     q = __shfl_sync(FULL, q, 0);
     if (q >= n_long) break;
     const float4 ray = s_ray[q];
-    const float r = rm_march_coop(mv, max_range, ray.x, ray.y, ray.z, ray.w, s_t[q]);
-    if (lane == 0) s_res[s_slot[q]] = r;
+    const float res = rm_march_coop(mv, max_range, ray.x, ray.y, ray.z, ray.w, s_t[q]);
+    if (lane == 0) s_res[s_slot[q]] = res;
   }
   __syncthreads();
-  if (active) result = s_res[threadIdx.x];
-  return result;
+  if (r.alive) return s_res[threadIdx.x];
+  return active ? rm_result(W, H, max_range, r) : max_range;
 }
 
 // pose -> ray; `ok` false for non-finite poses and for max_range <= 0 (the reference's loop body
@@ -861,44 +909,6 @@ bl_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
 //    in flight per warp at the same occupancy.
 // Arithmetic per step is rm_step's, i.e. the reference's.
 // ------------------------------------------------------------------------------------------
-struct RmSlot {
-  float x0, y0, dx, dy, t;
-  int id;
-  bool busy;   // the slot holds a ray (marching, or ended and not yet written out)
-  bool alive;  // ... and it is still marching
-};
-
-template <bool COND_LOAD>
-__device__ __forceinline__ void rm_step_pred(const float* __restrict__ dt, unsigned W, unsigned H, float max_range,
-                                             RmSlot& r) {
-  const int px = __float2int_rz(fadd(r.x0, fmul(r.dx, r.t)));
-  const int py = __float2int_rz(fadd(r.y0, fmul(r.dy, r.t)));
-  const bool go = r.alive && (unsigned)px < W && (unsigned)py < H;
-  // COND_LOAD: lanes that are not marching issue no load (ptxas makes it a BSSY / BRA / BSYNC triple, three
-  // more instructions per step); otherwise they read cell 0 and ignore it (one more 128-byte line in the
-  // request -- the gather rate of this kernel is bounded by L1 tag lookups, one line per clock per SM)
-  float d = 0.0f;
-  if (COND_LOAD) {
-    if (go) d = __ldg(dt + ((unsigned)px * H + (unsigned)py));
-  } else {
-    d = __ldg(dt + (go ? (unsigned)px * H + (unsigned)py : 0u));
-  }
-  const bool adv = go && !(d <= 0.0f);
-  const float tn = fadd(r.t, fmaxf(fmul(d, 0.999f), 1.0f));
-  r.t = adv ? tn : r.t;
-  r.alive = adv && (tn < max_range);
-}
-
-// result of a ray that ended with parameter t (see above); RangeLib.h:938-961
-__device__ __forceinline__ float rm_result(unsigned W, unsigned H, float max_range, const RmSlot& r) {
-  if (!(r.t < max_range)) return max_range;
-  const int px = __float2int_rz(fadd(r.x0, fmul(r.dx, r.t)));
-  const int py = __float2int_rz(fadd(r.y0, fmul(r.dy, r.t)));
-  if ((unsigned)px >= W || (unsigned)py >= H) return max_range;
-  const float xd = fsub((float)px, r.x0), yd = fsub((float)py, r.y0);
-  return __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
-}
-
 // PARK_REGS: the rays set up ahead of the march are parked one per lane in registers and handed out with
 // shuffles, instead of RL_QB per lane in shared memory: the kernel then uses no shared memory at all and the
 // whole 256 KB of the SM serves as L1 for the distance-map gathers (which are what bounds it: ncu shows the
@@ -1151,6 +1161,11 @@ static int sm_count() {
   return g_sm_count;
 }
 
+static int block_burst_pairs() {  // tuning knob of rm_march_block (RL_BLOCK_BURST_PAIRS), default RL_BLOCK_BURST / 2
+  static const int v = getenv("RL_BLOCK_BURST_PAIRS") ? max(1, atoi(getenv("RL_BLOCK_BURST_PAIRS"))) : RL_BLOCK_BURST / 2;
+  return v;
+}
+
 template <int KIND>
 static int launch_cast_kind(rl_method* m, int mode, const float* ins, const float* angles, const float* obs,
                             float* outs, double* weights, int n, int M, const PeerOut* peers) {
@@ -1164,6 +1179,7 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
   {
     const long long rays = (mode >= MODE_ANGLES) ? (long long)n * M : (long long)n;
     if (rays > 2LL * sm_count() * 7 * threads) mv.coop_threshold = 0;
+    mv.block_burst_pairs = block_burst_pairs();
   }
   if (mode == MODE_FUSED) {
     if (!m->d_table) {
@@ -1287,6 +1303,7 @@ static int launch_fused_beam_params_kind(rl_method* m, const float* ins, const B
   MapView mv = m->map_view();
   const int threads = 256;
   if ((long long)n * M > 2LL * sm_count() * 7 * threads) mv.coop_threshold = 0;  // as in launch_cast_kind
+  mv.block_burst_pairs = block_burst_pairs();
   const int chunk = min(M, 2048);
   const int ppb = max(1, min(threads / max(M, 1), 32));
   const int groups = (n + ppb - 1) / ppb;

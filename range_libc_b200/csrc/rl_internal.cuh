@@ -65,6 +65,7 @@ struct MapView {
   unsigned glt_td;
   float glt_td_div_2pi, glt_twopi_div_td;  // :1783-1784
   float glt_max_div_limits, glt_limits_div_max;  // :1785-1786
+  int block_burst_pairs = 6;  // rm_march_block: own-ray steps between two CTA-wide counts = 2 * this
 };
 
 struct CddtView {
@@ -183,7 +184,7 @@ struct rl_method {
   std::vector<float> h_radial;
 
   size_t dt_elems() const { return (size_t)W * H; }
-  int coop_threshold = 16;
+  int coop_threshold = 8;
   int persist = 1;  // RM large batches: 0 one ray per thread, 1 persistent warps with lane re-queuing
   rl::MapView map_view() const {
     rl::MapView v{W, H, d_occ, d_bits_t, tiles8_y(), d_dt, coop_threshold, d_glt, td, 0.f, 0.f, 0.f, 0.f};
