@@ -709,3 +709,33 @@ def test_fuzz_small_random_maps_all_kinds():
             assert_bit_equal(w, o.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs), what + " fused")
             meth.eval_sensor_model(obs, fan, w, len(angles), len(parts))
             assert_bit_equal(w, o.eval_sensor_model(obs, fan, len(angles), len(parts)), what + " two-step")
+
+
+def test_peer_store_epilogue_single_gpu_all_launch_shapes():
+    """The multi-GPU epilogue (weights stored through peer pointers at an offset into a gathered array) with this
+    GPU as its own only peer, for each fused launch shape: small (fused_kernel + cooperative tail), deep with many
+    particles per group (fused_rm_persist_kernel), deep with ~1000-beam particles (fused_kernel), and a big cloud on
+    a map beyond the L2 threshold (processing order permuted by rl_sort.cu)."""
+    import torch
+    cases = [("basement_hallways_5cm", 900, 60), ("basement_hallways_5cm", 12000, 60),
+             ("basement_hallways_5cm", 700, 1080), (4096, 40000, 16)]
+    for name, n, m_beams in cases:
+        occ = wl.synthetic_map(name, seed=5) if isinstance(name, int) else wl.load_map(name)
+        meth = make("rm", occ)
+        table = wl.sensor_table(501)
+        meth.set_sensor_model(table)
+        parts = wl.pf_particles_uniform(occ, n, seed=3)
+        angles = wl.lidar_angles(m_beams)
+        obs = np.linspace(10.0, 300.0, m_beams).astype(np.float32)
+        o = port.Oracle(port.RM, occ, MR, threads=8)
+        o.set_sensor_model(table)
+        want = o.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs)
+        offset = 17
+        gathered = torch.full((n + 40,), -1.0, dtype=torch.float64, device="cuda")
+        meth.calc_range_repeat_angles_eval_sensor_model_peers(
+            torch.from_numpy(parts).cuda(), torch.from_numpy(angles).cuda(), torch.from_numpy(obs).cuda(),
+            [gathered.data_ptr()], offset)
+        meth.synchronize()
+        got = gathered.cpu().numpy()
+        assert_bit_equal(got[offset:offset + n], want, "peer epilogue %s %dx%d" % (name, n, m_beams))
+        assert (got[:offset] == -1.0).all() and (got[offset + n:] == -1.0).all()
