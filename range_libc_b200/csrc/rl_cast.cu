@@ -6,13 +6,16 @@
 //                             ANGLES RangeMethod::numpy_calc_range_angles RangeLib.h:482-520
 //                             RM marches at CTA level (rm_march_block: own-ray bursts, then the last live
 //                             rays are finished cooperatively, one per warp)
-//   rm_persist_kernel<MODE>   RM, launches many waves deep: persistent warps with lane re-queuing; also fills
-//                             the GiantLUT table (MODE_GLT_BUILD)
-//   fused_kernel<KIND>        RangeMethod::calc_range_repeat_angles_eval_sensor_model :558-612
+//   rm_persist_kernel<MODE,..> RM, launches many waves deep: persistent warps with lane re-queuing, predicated
+//                             straight-line step bursts, no shared memory; also fills the GiantLUT table
+//                             (MODE_GLT_BUILD)
+//   fused_kernel<KIND,..>     RangeMethod::calc_range_repeat_angles_eval_sensor_model :558-612
 //                             a CTA owns whole particles; ranges go straight to the sensor
 //                             table lookup, the per-particle product is formed in the
 //                             reference's order (beam 0..M-1) so weights are bit-identical;
 //                             multi-GPU epilogues (peer stores, epoch flags) live here too
+//   fused_rm_persist_kernel   the same call for RM clouds many waves deep: re-queuing inside particle groups
+//   radial_kernel<KIND>       RangeMethod::calc_range_many_radial_optimized :616-676 (CDDT calc_range_pair)
 //   eval_sensor_kernel        RangeMethod::eval_sensor_model              RangeLib.h:533-555
 //
 // KIND: RL_BL (:696-769), RL_RM (:927-962), RL_CDDT / RL_PCDDT (:1342-1516), RL_GLT (:1869-1880).
