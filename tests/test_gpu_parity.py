@@ -224,14 +224,24 @@ def test_rm_persistent_kernel_large_batches(variant):
     meth.set_persistent(variant)
     o = port.Oracle(port.RM, occ, MR, threads=8)
     o.set_world(*world)
+    import torch
     n = 1_000_003  # not a multiple of anything
     q = wl.random_queries(W, H, n, seed=31)
+    want = o.calc_range_many(q)
     out = np.empty(n, np.float32)
-    meth.calc_range_many_grid(q, out)
-    assert_bit_equal(out, o.calc_range_many(q), "grid")
+    meth.calc_range_many_grid(q, out)  # host arrays: staged through device memory
+    assert_bit_equal(out, want, "grid (host)")
+    d_out = torch.empty(n, dtype=torch.float32, device="cuda")
+    meth.calc_range_many_grid(torch.from_numpy(q).cuda(), d_out)  # device arrays: one launch of the persistent kernel
+    meth.synchronize()
+    assert_bit_equal(d_out.cpu().numpy(), want, "grid (device)")
     qw = wl.grid_to_world(q, world[0], world[2], world[3])
+    want = o.numpy_calc_range(qw)
     meth.calc_range_many(qw, out)
-    assert_bit_equal(out, o.numpy_calc_range(qw), "world")
+    assert_bit_equal(out, want, "world (host)")
+    meth.calc_range_many(torch.from_numpy(qw).cuda(), d_out)
+    meth.synchronize()
+    assert_bit_equal(d_out.cpu().numpy(), want, "world (device)")
     parts = wl.grid_to_world(wl.random_queries(W, H, 9001, seed=32), world[0], world[2], world[3])
     angles = wl.lidar_angles(113)
     out = np.empty(len(parts) * len(angles), np.float32)
