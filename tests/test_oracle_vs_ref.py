@@ -123,3 +123,41 @@ def test_fuzz_small_random_maps_rm_cddt():
             else:
                 for a, b in zip(o.cddt_table(), r.cddt_table(td)):
                     assert_bit_equal(a, b, what + " table")
+
+
+def test_fuzz_radial_optimized_and_giant_lut_small_maps():
+    """calc_range_many_radial_optimized (pairs from CDDTCast::calc_range_pair) and GiantLUTCast on random small maps
+    against the unmodified reference.  Poses stay inside the map (the reference indexes its tables without bounds
+    checks outside it) and its output buffer is padded: it writes second beams past the row (RangeLib.h:665)."""
+    rng = np.random.default_rng(77)
+    for it in range(25):
+        occ = _random_small_map(rng)
+        W, H = occ.shape
+        mr = float(rng.choice([20.0, 50.0, 500.0]))
+        td = int(rng.choice([8, 16, 108, 120]))
+        n = 40
+        parts = np.empty((n, 3), np.float32)
+        parts[:, 0] = rng.uniform(0.5, H - 1.5, n)  # world x runs along the map's height (x/y swap, RangeLib.h:475)
+        parts[:, 1] = rng.uniform(0.5, W - 1.5, n)
+        parts[:, 2] = rng.uniform(-7, 7, n)
+        num_rays = int(rng.choice([7, 12, 37, 60, 100]))
+        lo, hi = sorted(rng.uniform(-3.1, 3.1, 2))
+        if hi - lo < 0.5:
+            hi = lo + 0.5
+        for kind in (ref.CDDT, ref.PCDDT, ref.RM):
+            r = ref.RefMethod(kind, ref.RefMap(occ=occ), mr, td)
+            o = port.Oracle(kind, occ, mr, td)
+            pad = 8 * num_rays + 4096
+            a = np.full(n * num_rays + pad, -7.0, np.float32)
+            b = a.copy()
+            r.calc_range_many_radial_optimized(num_rays, float(lo), float(hi), parts, a)
+            o.calc_range_many_radial_optimized(num_rays, float(lo), float(hi), parts, b)
+            # rows the reference overran into are rewritten by their own particle, except past the last row
+            assert_bit_equal(b[: n * num_rays], a[: n * num_rays],
+                             "iter %d kind %d %dx%d rays %d fan [%.2f, %.2f]" % (it, kind, W, H, num_rays, lo, hi))
+        if W * H * td <= 400000:
+            q = wl.random_queries(W, H, 300, seed=it)
+            r = ref.RefMethod(ref.GLT, ref.RefMap(occ=occ), mr, td)
+            o = port.Oracle(port.GLT, occ, mr, td)
+            assert np.array_equal(r.glt_table(td), o.glt_table()), "glt table iter %d" % it
+            assert_bit_equal(o.calc_range_many(q), r.calc_range_many(q), "glt iter %d" % it)
