@@ -28,6 +28,27 @@
 
 namespace rl {
 
+// Development aid (tools/trace_fused.py builds a separate library with -DRL_TRACE; the product library never
+// defines it): per-CTA globaltimer stamps at the phase boundaries of the small fused launch.
+#ifdef RL_TRACE
+__device__ unsigned long long* g_rl_trace = nullptr;
+__device__ __forceinline__ void rl_trace_mark(int slot) {
+  if (g_rl_trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_rl_trace[(size_t)blockIdx.x * 16 + slot] = t;
+  }
+}
+__device__ __forceinline__ void rl_trace_value(int slot, unsigned long long v) {
+  if (g_rl_trace && threadIdx.x == 0) g_rl_trace[(size_t)blockIdx.x * 16 + slot] = v;
+}
+#define RL_TRACE_MARK(slot) rl_trace_mark(slot)
+#define RL_TRACE_VALUE(slot, v) rl_trace_value(slot, (unsigned long long)(v))
+#else
+#define RL_TRACE_MARK(slot)
+#define RL_TRACE_VALUE(slot, v)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // single-ray device functions
 // ------------------------------------------------------------------------------------------
@@ -211,6 +232,7 @@ __device__ __forceinline__ float rm_march_block(const MapView& mv, float max_ran
     s_n = 0;
     s_next = 0;
   }
+  RL_TRACE_MARK(1);
   for (int steps = 2 * mv.block_burst_pairs;; steps += 2 * mv.block_burst_pairs) {
     if (__any_sync(FULL, r.alive)) {
 #pragma unroll 1
@@ -220,6 +242,13 @@ __device__ __forceinline__ float rm_march_block(const MapView& mv, float max_ran
       }
     }
     const int alive = __syncthreads_count(r.alive);
+    if (steps == 2 * mv.block_burst_pairs) {
+      RL_TRACE_MARK(2);
+      RL_TRACE_VALUE(9, alive);
+    }
+    RL_TRACE_MARK(3);
+    RL_TRACE_VALUE(8, steps);
+    RL_TRACE_VALUE(10, alive);
     if (alive == 0) return active ? rm_result(W, H, max_range, r) : max_range;
     // few rays left -- or, after 24 steps, a moderate number of rays that are evidently long ones
     if (alive <= handoff || (steps >= 24 && alive <= 4 * handoff)) break;
@@ -242,6 +271,7 @@ __device__ __forceinline__ float rm_march_block(const MapView& mv, float max_ran
     if (lane == 0) s_res[s_slot[q]] = res;
   }
   __syncthreads();
+  RL_TRACE_MARK(5);
   if (r.alive) return s_res[threadIdx.x];
   return active ? rm_result(W, H, max_range, r) : max_range;
 }
@@ -677,6 +707,7 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
              typename std::conditional<PARAM_BEAMS, BeamParams, NoBeamParams>::type beams,
              const int* __restrict__ perm) {
   extern __shared__ double vals[];
+  RL_TRACE_MARK(0);
   __shared__ float s_beams[PARAM_BEAMS ? 2 * RL_PARAM_BEAMS : 1];
   if (PARAM_BEAMS) {
     const BeamParams& bp = reinterpret_cast<const BeamParams&>(beams);
@@ -738,11 +769,13 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
         }
       }
       __syncthreads();
+      RL_TRACE_MARK(6);
       if (threadIdx.x < np) {
         const double* v = vals + threadIdx.x * cm;
         for (int a = 0; a < cm; ++a) w = __dmul_rn(w, v[a]);  // reference order: beam ascending
       }
       __syncthreads();
+      RL_TRACE_MARK(7);
     }
     if (threadIdx.x < np) {
       const size_t i = perm ? (size_t)__ldg(perm + p0 + threadIdx.x) : (size_t)(p0 + threadIdx.x);
@@ -1418,3 +1451,9 @@ int launch_sincosf(const float* x, float* s, float* c, int n, cudaStream_t st) {
 }
 
 }  // namespace rl
+
+#ifdef RL_TRACE
+extern "C" int rl_debug_set_trace(void* device_buffer) {
+  return cudaMemcpyToSymbol(rl::g_rl_trace, &device_buffer, sizeof(void*)) == cudaSuccess ? 0 : -2;
+}
+#endif
