@@ -249,3 +249,17 @@ cdef class PyCDDTCast(_Method):
 cdef class PyGiantLUTCast(_Method):
     def __cinit__(self, PyOMap Map, float max_range, unsigned int theta_disc):
         self._create(RL_GLT, Map, max_range, theta_disc)
+
+
+cdef class PyNull:
+    """The reference's call-overhead dummy (RangeLibc.pyx:342-352): touches its arguments, computes nothing."""
+    def __cinit__(self, PyOMap Map, float max_range, unsigned int theta_disc):
+        pass
+
+    cpdef float calc_range(self, float x, float y, float heading):
+        return x + y + heading
+
+    cpdef calc_range_many(self, float[:, ::1] ins, float[::1] outs):
+        a = ins[0, 0]
+        b = outs[0]
+        c = outs.shape[0]

@@ -98,3 +98,32 @@ def test_cpp_header_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
                            "-lrangelib_b200", "-Wl,-rpath," + libdir])
     rc = subprocess.run([exe], capture_output=True, text=True)
     assert rc.returncode == (0 if torch.cuda.is_available() else 3), rc.stdout + rc.stderr
+
+
+def test_cython_drop_in_exposes_the_reference_module_surface():
+    """`range_libc` (pywrapper/RangeLibc.pyx) must import without a GPU and carry every class, method and module
+    constant a caller of the reference's module can name (RangeLibc.pyx:94-352 of the reference)."""
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "range_libc_b200", "pywrapper"))
+    try:
+        import range_libc as m
+    except ImportError:
+        import pytest
+        pytest.skip("Cython extension not built")
+    for const in ("USE_CACHED_TRIG", "USE_ALTERNATE_MOD", "USE_CACHED_CONSTANTS", "USE_FAST_ROUND", "NO_INLINE", "USE_LRU_CACHE",
+                  "LRU_CACHE_SIZE", "SHOULD_USE_CUDA"):
+        assert hasattr(m, const), const
+    common = ["calc_range", "calc_range_many", "calc_range_repeat_angles", "calc_range_repeat_angles_eval_sensor_model",
+              "eval_sensor_model", "set_sensor_model"]
+    surface = {"PyOMap": ["save", "isOccupied", "error", "width", "height"],
+               "PyBresenhamsLine": common + ["saveTrace"], "PyRayMarching": common + ["saveTrace"],
+               "PyRayMarchingGPU": common, "PyCDDTCast": common + ["prune", "calc_range_many_radial_optimized"],
+               "PyGiantLUTCast": common, "PyNull": ["calc_range", "calc_range_many"]}
+    for cls, methods in surface.items():
+        assert hasattr(m, cls), cls
+        for name in methods:
+            assert hasattr(getattr(m, cls), name), "%s.%s" % (cls, name)
+    omap = m.PyOMap(np.zeros((3, 4), dtype=bool))  # arr[row = y, col = x]
+    assert (omap.width(), omap.height()) == (4, 3) and not omap.isOccupied(1, 1) and not omap.error()
