@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librangelib_b200.so")
+# RL_B200_LIB: development aid -- load an alternative build of the same library (tools/trace_fused.py, A/B builds)
+LIB_PATH = os.environ.get("RL_B200_LIB") or os.path.join(_HERE, "librangelib_b200.so")
 
 RL_BL, RL_RM, RL_CDDT, RL_PCDDT, RL_GLT = 0, 1, 2, 3, 4
 RL_OK, RL_E_INVALID, RL_E_CUDA, RL_E_NO_DEVICE, RL_E_STATE, RL_E_MIXED = 0, -1, -2, -3, -4, -5
