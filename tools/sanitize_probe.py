@@ -34,3 +34,34 @@ for ctor in (lambda: rl.PyRayMarchingGPU(omap, 256.0), lambda: rl.PyBresenhamsLi
     m.update_map_batch(np.ones(64, np.uint8), np.array([[8, 8, 8, 8]], np.int32))
     m.calc_range_many_grid(q, out)
     print(type(m).__name__, "ok", float(out.mean()))
+
+# paths added later in round 1 (not yet run under the sanitizer: the round's GPU budget was spent)
+import torch  # noqa: E402
+
+rm = rl.PyRayMarchingGPU(omap, 256.0)
+rm.set_sensor_model(table)
+cd = rl.PyCDDTCast(omap, 256.0, 24)
+fan = np.full(len(parts) * 37, -1.0, np.float32)
+for m in (rm, cd):  # radial_kernel / cddt_cast_pair
+    m.calc_range_many_radial_optimized(37, -1.0, 2.0, parts, fan)
+# deep fused update: fused_rm_persist_kernel (lane re-queuing inside particle groups)
+big = wl.pf_particles_uniform(occ, 12000, seed=3)
+wb = np.empty(len(big), np.float64)
+rm.calc_range_repeat_angles_eval_sensor_model(big, angles, obs, wb)
+# large independent batch on device pointers: rm_persist_kernel (parked rays in registers)
+qd = torch.from_numpy(wl.random_queries(W, H, 600000, seed=4)).cuda()
+od = torch.empty(len(qd), dtype=torch.float32, device="cuda")
+rm.calc_range_many_grid(qd, od)
+rm.synchronize()
+# whole-map ingest kernels
+img = np.random.default_rng(5).integers(0, 256, (H, W, 4), dtype=np.uint8)
+rm.set_map_rgba(img, 128.0)
+cd.set_map_occupancy_grid(np.random.default_rng(6).integers(-1, 101, (W, H)).astype(np.int8))
+# spatial ordering (rl_sort.cu): needs a structure beyond the L2 threshold, i.e. a map of >= 3548^2 cells
+occ_big = wl.synthetic_map(3600, seed=7)
+rmb = rl.PyRayMarchingGPU(rl.PyOMap(np.ascontiguousarray(occ_big.T.astype(bool))), 256.0)
+rmb.set_sensor_model(table)
+cloud = wl.pf_particles_uniform(occ_big, 33000, seed=8)
+wc = np.empty(len(cloud), np.float64)
+rmb.calc_range_repeat_angles_eval_sensor_model(cloud, angles[:4].copy(), obs[:4].copy(), wc)
+print("late round-1 paths ok", float(fan.max()), float(wb.mean()), float(od.mean().item()), float(wc.mean()))
