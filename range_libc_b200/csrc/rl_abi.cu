@@ -217,7 +217,7 @@ class Marshal {
 // Per-transfer latency is what costs here, so: the poses cross PCIe in one async copy straight from the caller's
 // buffer when it is pinned (through the pinned staging buffer otherwise); angles and observation travel inside the
 // kernel launch (rl::BeamParams); the kernel stores the weights directly into pinned host memory (the caller's
-// buffer if pinned).  Measured on B200, 4000 x 60 RM: 47.1 -> 42.7 us per blocking call (tools/e2e_probe.py).
+// buffer if pinned).  Measured on B200, 4000 x 60 RM: 47.1 -> 42.7 us per blocking call (tests/probes/e2e_probe.py).
 // Also measured and dropped: CTAs fetching their poses from mapped host memory instead of the copy (56 us: a
 // thousand 48-byte PCIe reads), and a completion flag in host memory raised by the last CTA after a system-scope
 // fence instead of the stream synchronisation (+2 us).

@@ -1,13 +1,13 @@
 """How close are the reference's own CUDA kernels (oracle/_ref/libref_cuda.so: kernels.cu for sm_100a) to the
 reference's CPU RayMarching (STRICT build) and to this library?  Prints agreement statistics and timings.
-Run on a GPU box: python tools/rmgpu_probe.py"""
+Run on a GPU box: python tests/probes/rmgpu_probe.py"""
 import os
 import sys
 import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import range_libc_b200 as rl  # noqa: E402
 from oracle import ref  # noqa: E402
