@@ -92,8 +92,12 @@ __device__ __forceinline__ bool rm_step(const MapView& mv, float max_range, floa
 // starts the next batch there; lane 0 always probes the exact current sample, so every batch
 // advances at least one step.  Arithmetic and step sequence are the reference's, untouched:
 // the probes are a register-resident cache, never a source of different values.
+#ifndef RL_COOP_SPACING
 #define RL_COOP_SPACING 0.75f
-#define RL_COOP_PROBES 2         // probes per lane and batch: 64 probes = 48 px of ray per L2 round trip
+#endif
+#ifndef RL_COOP_PROBES
+#define RL_COOP_PROBES 2  // probes per lane and batch: 64 probes = 48 px of ray per L2 round trip
+#endif
 #define RL_STEP_INF 0x7f800000u  // +inf in the per-lane step table: "obstacle here" -- and the value of "no probe"
 __device__ __forceinline__ float rm_march_coop(const MapView& mv, float max_range, float x0, float y0, float dx,
                                                float dy, float t) {
@@ -203,7 +207,9 @@ __device__ __forceinline__ float rm_result(unsigned W, unsigned H, float max_ran
 //            launch -- thus run concurrently on different warps, each at the cooperative rate, instead of
 //            holding a nearly empty warp each.
 // mv.coop_threshold == 0 (or a map / range too large for the 16-bit cell keys) keeps everything in phase 1.
+#ifndef RL_BLOCK_BURST
 #define RL_BLOCK_BURST 12
+#endif
 __device__ __forceinline__ float rm_march_block(const MapView& mv, float max_range, bool active, float x0, float y0,
                                                 float dx, float dy) {
   __shared__ float4 s_ray[256];
@@ -924,7 +930,9 @@ bl_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
 // In-flight rays keep their state in registers across a setup phase, so nothing drains between
 // batches and the marching loop runs with most lanes busy until the chunk is exhausted.
 // ------------------------------------------------------------------------------------------
-#define RL_QB 4  // parked rays per lane and setup phase
+#ifndef RL_QB
+#define RL_QB 4  // parked rays per lane and setup phase (shared-memory variant)
+#endif
 #ifndef RL_FUSED_GROUP_RAYS
 #define RL_FUSED_GROUP_RAYS 4096  // rays of one particle group in fused_rm_persist_kernel (2048: -8 %, 6144: -30 %)
 #endif
