@@ -89,8 +89,10 @@ int rl_method_synchronize(rl_method* m);
  * on it (BL: bit grid only; RM: distance transform rebuilt; CDDT: table rebuilt).
  * patch may be host or device memory. */
 int rl_method_update_map(rl_method* m, const uint8_t* patch_xmajor, int x0, int y0, int w, int h);
-/* the same for n non-overlapping patches in ONE launch: rects = n x (x0, y0, w, h) (HOST ints); the
- * patches' bytes are concatenated in `patches` (HOST or DEVICE), each x-major inside its rectangle. */
+/* the same for n patches in one call (two launches: all cells, then the bit tiles they touch): rects = n x
+ * (x0, y0, w, h) (HOST ints); the patches' bytes are concatenated in `patches` (HOST or DEVICE), each x-major
+ * inside its rectangle.  Patches must not overlap cell-wise (checked for n <= 4096; RL_E_INVALID); they need not
+ * be 8-aligned and may share a bit tile. */
 int rl_method_update_map_batch(rl_method* m, const uint8_t* patches_xmajor, const int* rects, int n);
 /* Whole-map ingest on the device: replace the occupancy of an existing handle (same size) from a source image in
  * HOST or DEVICE memory and refresh the kind's structures -- a mapping pipeline that keeps its grid in HBM never
@@ -170,6 +172,16 @@ int rl_calc_range_repeat_angles_eval_sensor_model_signalled(rl_method* m, const 
                                                             const float* obs, int64_t offset, int num_particles,
                                                             int num_angles, int* buffer_index);
 int rl_method_peers_wait(rl_method* m);
+/* The sharded particle-filter update as ONE blocking call with HOST buffers (what a multi-process particle filter
+ * written against the reference's calc_range_repeat_angles_eval_sensor_model would call on each rank; replaces the
+ * loop RangeLib.h:558-612 over ALL particles): this rank's `num_particles` poses (the slice starting at particle
+ * `offset` of `n_total`) are copied to the device, the signalled fused kernel computes their weights and stores them
+ * into every rank's gathered array over NVLink, and after every rank's slice has arrived the whole gathered array
+ * (n_total doubles) is copied into weights_all.  Needs rl_method_peers_init; every rank must call it the same number
+ * of times.  With DEVICE pointers nothing blocks: the copy into weights_all is device-to-device on the handle's stream. */
+int rl_calc_range_repeat_angles_eval_sensor_model_sharded(rl_method* m, const float* ins, const float* angles,
+                                                          const float* obs, double* weights_all, int64_t offset,
+                                                          int num_particles, int num_angles, int64_t n_total);
 
 /* ---- table-level access for parity tests ---------------------------------------------------- */
 /* the occupancy bytes resident on the device, x-major out[x*H+y] (after dynamic updates / device ingest). out: HOST */
@@ -188,6 +200,9 @@ int rl_debug_set_coop_threshold(rl_method* m, int rays);
 /* tuning knob (RM): large batches use persistent warps with lane re-queuing (default 1) or the
  * one-ray-per-thread kernel (0).  Results are identical. */
 int rl_debug_set_persistent(rl_method* m, int on);
+/* tuning knob (fused call, clouds >= 32768 particles on structures larger than L2): process the particles in the
+ * order of the 64x64-cell tile they stand in (default 1) or in caller order (0).  Results are identical. */
+int rl_debug_set_spatial_sort(rl_method* m, int on);
 /* GiantLUTCast::giant_lut (RangeLib.h:1903) as out[(x*H + y)*td + i], W*H*td uint16; HOST buffer */
 int rl_debug_glt_dump(rl_method* m, uint16_t* out);
 /* device trig used by BL/RM (restated glibc sinf/cosf); HOST buffers; for tests */

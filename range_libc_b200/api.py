@@ -97,6 +97,12 @@ class PyOMap:
         check(lib().rl_map_get(self._h, C.c_void_p(out.ctypes.data)))
         return out
 
+    def save(self, fn):
+        """OMap::save (RangeLib.h:264-291): RGBA PNG, occupied cells black, free cells white.  Returns False on
+        success, like the reference (whose return value is lodepng's error code)."""
+        from .mapio import save_png
+        return save_png(fn, self.grid())
+
     def update(self, patch_xmajor, x0, y0):
         """Dynamic maps: overwrite a [w, h] x-major patch of the HOST map (see RangeMethod.update_map)."""
         p = np.ascontiguousarray(patch_xmajor, dtype=np.uint8)
@@ -201,6 +207,19 @@ class _RangeMethod:
     def peers_wait(self):
         check(lib().rl_method_peers_wait(self._h))
 
+    def calc_range_repeat_angles_eval_sensor_model_sharded(self, ins, angles, obs, weights_all, offset):
+        """The sharded update as one call: `ins` are this rank's particles (the slice of the cloud starting at
+        particle `offset`), `weights_all` (f64[n_total]) receives the weights of ALL particles.  Host arrays:
+        blocking; device tensors: asynchronous on the handle's stream.  Needs peers_init."""
+        pi, si = _buf(ins, np.float32, 2, "ins")
+        pa, sa = _buf(angles, np.float32, 1, "angles")
+        pb, sb = _buf(obs, np.float32, 1, "obs")
+        pw, sw = _buf(weights_all, np.float64, 1, "weights_all")
+        if si[1] != 3 or sb[0] < sa[0] or sw[0] < int(offset) + si[0]:
+            raise ValueError("shape mismatch")
+        check(lib().rl_calc_range_repeat_angles_eval_sensor_model_sharded(self._h, pi, pa, pb, pw, int(offset), si[0],
+                                                                          sa[0], sw[0]))
+
     def eval_sensor_model(self, observation, ranges, outs, num_rays, num_particles):
         pb, sb = _buf(observation, np.float32, 1, "observation")
         pr, sr = _buf(ranges, np.float32, 1, "ranges")
@@ -281,6 +300,10 @@ class _RangeMethod:
     def set_persistent(self, on):
         """Tuning knob (RM): persistent-warp kernel with lane re-queuing for large batches."""
         check(lib().rl_debug_set_persistent(self._h, int(on)))
+
+    def set_spatial_sort(self, on):
+        """Tuning knob: tile-ordered processing of big clouds on > L2 structures (default on).  Results are identical."""
+        check(lib().rl_debug_set_spatial_sort(self._h, 1 if on else 0))
 
     def set_coop_threshold(self, rays):
         """Tuning knob (RM, small launches): a CTA with <= rays live rays finishes them cooperatively (0 = off)."""

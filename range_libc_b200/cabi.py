@@ -51,6 +51,7 @@ SIGNATURES = {
     "rl_method_peers_init": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i]),
     "rl_calc_range_repeat_angles_eval_sensor_model_signalled": (_i, [_vp, _vp, _vp, _vp, C.c_int64, _i, _i, C.POINTER(_i)]),
     "rl_method_peers_wait": (_i, [_vp]),
+    "rl_calc_range_repeat_angles_eval_sensor_model_sharded": (_i, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _i, _i, C.c_int64]),
     "rl_debug_get_dt": (_i, [_vp, _vp]),
     "rl_debug_cddt_dims": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, _vp]),
     "rl_debug_cddt_dump": (_i, [_vp, _vp, _vp]),
@@ -58,6 +59,7 @@ SIGNATURES = {
     "rl_debug_sincosf": (_i, [_vp, _vp, _vp, _i]),
     "rl_debug_set_coop_threshold": (_i, [_vp, _i]),
     "rl_debug_set_persistent": (_i, [_vp, _i]),
+    "rl_debug_set_spatial_sort": (_i, [_vp, _i]),
 }
 
 _lib = None

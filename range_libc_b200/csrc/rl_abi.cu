@@ -76,14 +76,36 @@ static int ensure_host_stage(rl_method* m, size_t bytes) {
   return RL_OK;
 }
 
-static int bind(rl_method* m) {
-  if (!m) {
-    set_error("null method handle");
-    return RL_E_INVALID;
+// Makes the handle's device current for the duration of one ABI call and restores the caller's device on exit,
+// so a process that drives several GPUs from one thread does not find its current device changed by this library.
+class DeviceGuard {
+ public:
+  ~DeviceGuard() {
+    if (switched_) cudaSetDevice(prev_);
   }
-  RL_CUDA(cudaSetDevice(m->device));
-  return RL_OK;
-}
+  int bind(int device) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) {
+      cudaGetLastError();
+      prev_ = device;
+    }
+    if (prev_ != device) {
+      RL_CUDA(cudaSetDevice(device));
+      switched_ = true;
+    }
+    return RL_OK;
+  }
+  int bind(rl_method* m) {
+    if (!m) {
+      set_error("null method handle");
+      return RL_E_INVALID;
+    }
+    return bind(m->device);
+  }
+
+ private:
+  int prev_ = 0;
+  bool switched_ = false;
+};
 
 // Marshals the data pointers of one call.
 //   all device             -> run in place, asynchronous
@@ -256,7 +278,8 @@ static int run_fused_host_small(rl_method* m, const float* ins, const float* ang
 // Common driver for the four batched cast entry points.
 static int run_cast(rl_method* m, int mode, const float* ins, const float* angles, const float* obs, float* outs,
                     double* weights, int n, int M) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (n < 0 || M < 0) {
     set_error("negative count");
@@ -319,7 +342,8 @@ static int replace_map(rl_method* m, const void* src, size_t bytes, F ingest) {
 
 static void free_method(rl_method* m) {
   if (!m) return;
-  cudaSetDevice(m->device);
+  DeviceGuard dg;
+  dg.bind(m->device);
   cddt_free(m);
   sort_free(m);
   cudaFree(m->d_occ);
@@ -423,7 +447,11 @@ int rl_method_create(int kind, const rl_map* map, float max_range, unsigned td, 
     set_error("rangelib_b200 is built for sm_100a only; this device is not a B200-class GPU");
     return RL_E_NO_DEVICE;
   }
-  RL_CUDA(cudaSetDevice(device));
+  DeviceGuard dg;
+  {
+    const int rc0 = dg.bind(device);
+    if (rc0) return rc0;
+  }
   rl_method* m = new rl_method();
   m->kind = kind;
   m->device = device;
@@ -467,7 +495,8 @@ int rl_method_create(int kind, const rl_map* map, float max_range, unsigned td, 
 void rl_method_destroy(rl_method* m) { free_method(m); }
 
 int rl_method_prune(rl_method* m, float max_range) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (m->kind != RL_CDDT && m->kind != RL_PCDDT) {
     set_error("prune is only defined for CDDT");
@@ -489,14 +518,16 @@ int rl_method_use_own_stream(rl_method* m) {
 }
 
 int rl_method_synchronize(rl_method* m) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   RL_CUDA(cudaStreamSynchronize(m->stream));
   return RL_OK;
 }
 
 int rl_method_update_map(rl_method* m, const uint8_t* patch, int x0, int y0, int w, int h) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (!patch || x0 < 0 || y0 < 0 || w <= 0 || h <= 0 || x0 + w > m->W || y0 + h > m->H) {
     set_error("rl_method_update_map: patch outside the map");
@@ -515,7 +546,8 @@ int rl_method_update_map(rl_method* m, const uint8_t* patch, int x0, int y0, int
 }
 
 int rl_method_set_map_occupancy_grid(rl_method* m, const int8_t* data, int rows, int cols) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (rows != m->W || cols != m->H || (!data && (size_t)rows * cols > 0)) {
     set_error("rl_method_set_map_occupancy_grid: need data[rows][cols] with rows == map width and cols == map height");
@@ -525,7 +557,8 @@ int rl_method_set_map_occupancy_grid(rl_method* m, const int8_t* data, int rows,
 }
 
 int rl_method_set_map_rgba(rl_method* m, const uint8_t* rgba, int img_w, int img_h, float threshold) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (img_w != m->W || img_h != m->H || (!rgba && (size_t)img_w * img_h > 0)) {
     set_error("rl_method_set_map_rgba: image size differs from the map's");
@@ -546,8 +579,15 @@ int rl_debug_set_persistent(rl_method* m, int on) {
   return RL_OK;
 }
 
+int rl_debug_set_spatial_sort(rl_method* m, int on) {
+  if (!m) return RL_E_INVALID;
+  m->spatial_sort = on;
+  return RL_OK;
+}
+
 int rl_method_update_map_batch(rl_method* m, const uint8_t* patches, const int* rects, int n) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (n < 0 || (n > 0 && (!patches || !rects))) {
     set_error("rl_method_update_map_batch: bad arguments");
@@ -564,6 +604,23 @@ int rl_method_update_map_batch(rl_method* m, const uint8_t* patches, const int* 
     }
     offsets[p] = total;
     total += (long long)w * h;
+  }
+  // cell-wise overlap makes the result depend on the CTA schedule: reject it (sweep over x-sorted rectangles;
+  // a frame of BASELINE config 4 has 64 patches -- beyond 4096 the caller's word is taken)
+  if (n <= 4096) {
+    std::vector<int> order(n);
+    for (int p = 0; p < n; ++p) order[p] = p;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return rects[4 * a] < rects[4 * b]; });
+    for (int i = 0; i < n; ++i) {
+      const int* a = rects + 4 * order[i];
+      for (int j = i + 1; j < n && rects[4 * order[j]] < a[0] + a[2]; ++j) {
+        const int* b = rects + 4 * order[j];
+        if (b[1] < a[1] + a[3] && a[1] < b[1] + b[3]) {
+          set_error("rl_method_update_map_batch: patches overlap");
+          return RL_E_INVALID;
+        }
+      }
+    }
   }
   // staging: [rects | offsets | patches (if on the host)]
   const size_t b_rects = align256(sizeof(int) * 4 * (size_t)n), b_off = align256(sizeof(long long) * (size_t)n);
@@ -612,7 +669,8 @@ int rl_numpy_calc_range_angles(rl_method* m, const float* ins, const float* angl
 }
 
 int rl_set_sensor_model(rl_method* m, const double* table, int k) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (!table || k <= 0) {
     set_error("set_sensor_model: bad table");
@@ -630,7 +688,8 @@ int rl_set_sensor_model(rl_method* m, const double* table, int k) {
 }
 
 int rl_eval_sensor_model(rl_method* m, const float* obs, const float* ranges, double* outs, int M, int n) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (n < 0 || M < 0) return RL_E_INVALID;
   if (n == 0) return RL_OK;
@@ -662,7 +721,8 @@ int rl_calc_range_repeat_angles_eval_sensor_model(rl_method* m, const float* ins
 // reference's types: float step, double index_offset narrowed to float, roundf).
 int rl_calc_range_many_radial_optimized(rl_method* m, const float* ins, float* outs, int n, int num_rays,
                                         float min_angle, float max_angle) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (n < 0 || num_rays < 2 || !std::isfinite(min_angle) || !std::isfinite(max_angle) || !(max_angle != min_angle)) {
     set_error("calc_range_many_radial_optimized: need n >= 0, num_rays >= 2 and finite min_angle != max_angle");
@@ -719,7 +779,8 @@ int rl_calc_range_many_radial_optimized(rl_method* m, const float* ins, float* o
 int rl_calc_range_repeat_angles_eval_sensor_model_peers(rl_method* m, const float* ins, const float* angles,
                                                         const float* obs, double* const* peer_weights, int n_peers,
                                                         int64_t offset, int n, int M) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (n < 0 || M < 0 || n_peers < 1 || n_peers > RL_MAX_PEERS || !peer_weights || offset < 0) {
     set_error("rl_calc_range_repeat_angles_eval_sensor_model_peers: bad arguments");
@@ -753,7 +814,8 @@ int rl_calc_range_repeat_angles_eval_sensor_model_peers(rl_method* m, const floa
 
 int rl_method_peers_init(rl_method* m, double* const* weights0, double* const* weights1, int64_t* const* flags,
                          int n_peers, int rank) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (!weights0 || !weights1 || !flags || n_peers < 1 || n_peers > RL_MAX_PEERS || rank < 0 || rank >= n_peers) {
     set_error("rl_method_peers_init: bad arguments");
@@ -790,7 +852,8 @@ int rl_method_peers_init(rl_method* m, double* const* weights0, double* const* w
 int rl_calc_range_repeat_angles_eval_sensor_model_signalled(rl_method* m, const float* ins, const float* angles,
                                                             const float* obs, int64_t offset, int n, int M,
                                                             int* buffer_index) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (!m->peers_ready) {
     set_error("rl_method_peers_init has not been called");
@@ -813,8 +876,61 @@ int rl_calc_range_repeat_angles_eval_sensor_model_signalled(rl_method* m, const 
   return RL_OK;
 }
 
+// The sharded particle-filter update through HOST pointers (one process per GPU): this rank's particles go to the
+// device, the fused kernel computes their weights and stores them into every rank's gathered array over NVLink
+// (signalled epilogue: the synchronisation is part of the same kernel), a wait kernel holds the stream until every
+// rank's slice has arrived, and the whole gathered array comes back to the caller's buffer.  Blocking, like every
+// host-pointer call.  With DEVICE pointers the same sequence is enqueued on the handle's stream and the gathered
+// array is copied device-to-device without synchronising.
+int rl_calc_range_repeat_angles_eval_sensor_model_sharded(rl_method* m, const float* ins, const float* angles,
+                                                          const float* obs, double* weights_all, int64_t offset, int n,
+                                                          int M, int64_t n_total) {
+  DeviceGuard dg;
+  int rc = dg.bind(m);
+  if (rc) return rc;
+  if (!m->peers_ready) {
+    set_error("rl_method_peers_init has not been called");
+    return RL_E_STATE;
+  }
+  if (n <= 0 || M <= 0 || offset < 0 || n_total < offset + n || !ins || !angles || !obs || !weights_all) {
+    set_error("sharded fused call: bad arguments (every rank must call with n > 0, num_angles > 0)");
+    return RL_E_INVALID;
+  }
+  const bool dev = is_device_ptr(ins);
+  if (dev != (bool)is_device_ptr(angles) || dev != (bool)is_device_ptr(obs) || dev != (bool)is_device_ptr(weights_all)) {
+    set_error("host and device pointers mixed in one call");
+    return RL_E_MIXED;
+  }
+  const float *d_ins = ins, *d_ang = angles, *d_obs = obs;
+  if (!dev) {
+    const size_t b_ins = align256(sizeof(float) * 3 * (size_t)n), b_m = align256(sizeof(float) * (size_t)M);
+    rc = ensure_stage(m, b_ins + 2 * b_m);
+    if (rc) return rc;
+    char* base = (char*)m->d_stage;
+    RL_CUDA(cudaMemcpyAsync(base, ins, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    RL_CUDA(cudaMemcpyAsync(base + b_ins, angles, sizeof(float) * (size_t)M, cudaMemcpyHostToDevice, m->stream));
+    RL_CUDA(cudaMemcpyAsync(base + b_ins + b_m, obs, sizeof(float) * (size_t)M, cudaMemcpyHostToDevice, m->stream));
+    d_ins = (const float*)base;
+    d_ang = (const float*)(base + b_ins);
+    d_obs = (const float*)(base + b_ins + b_m);
+  }
+  PeerOut po = m->peer_cfg;
+  po.offset = offset;
+  rc = launch_cast(m, MODE_FUSED, d_ins, d_ang, d_obs, nullptr, nullptr, n, M, &po);
+  if (rc) return rc;
+  m->host_epoch += 1;
+  rc = launch_peers_wait(m);
+  if (rc) return rc;
+  const double* gathered = (m->host_epoch & 1) ? po.ptr1[po.rank] : po.ptr[po.rank];
+  RL_CUDA(cudaMemcpyAsync(weights_all, gathered, sizeof(double) * (size_t)n_total,
+                          dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, m->stream));
+  if (!dev) RL_CUDA(cudaStreamSynchronize(m->stream));
+  return RL_OK;
+}
+
 int rl_method_peers_wait(rl_method* m) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (!m->peers_ready) {
     set_error("rl_method_peers_init has not been called");
@@ -824,7 +940,8 @@ int rl_method_peers_wait(rl_method* m) {
 }
 
 int rl_debug_get_occ(rl_method* m, uint8_t* out) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (!out) return RL_E_INVALID;
   const size_t n = (size_t)m->W * m->H;
@@ -834,7 +951,8 @@ int rl_debug_get_occ(rl_method* m, uint8_t* out) {
 }
 
 int rl_debug_get_dt(rl_method* m, float* out) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (m->kind != RL_RM || !m->d_dt || !out) {
     set_error("rl_debug_get_dt: not an RM method");
@@ -846,7 +964,8 @@ int rl_debug_get_dt(rl_method* m, float* out) {
 }
 
 int rl_debug_cddt_dims(rl_method* m, int64_t* n_bins, int64_t* n_values, int* widths, float* translations) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (m->kind != RL_CDDT && m->kind != RL_PCDDT) {
     set_error("not a CDDT method");
@@ -860,7 +979,8 @@ int rl_debug_cddt_dims(rl_method* m, int64_t* n_bins, int64_t* n_values, int* wi
 }
 
 int rl_debug_cddt_dump(rl_method* m, int64_t* offsets, float* values) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if ((m->kind != RL_CDDT && m->kind != RL_PCDDT) || !offsets || !values) {
     set_error("not a CDDT method");
@@ -874,7 +994,8 @@ int rl_debug_cddt_dump(rl_method* m, int64_t* offsets, float* values) {
 }
 
 int rl_debug_glt_dump(rl_method* m, uint16_t* out) {
-  int rc = bind(m);
+  DeviceGuard dg;
+  int rc = dg.bind(m);
   if (rc) return rc;
   if (m->kind != RL_GLT || !m->d_glt || !out) {
     set_error("rl_debug_glt_dump: not a GiantLUT method");

@@ -1194,15 +1194,17 @@ fused_rm_persist_kernel(MapView mv, WorldXform xf, SensorView sv, float max_rang
 // ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
-static int g_sm_count = 0;
+// SM count of the CURRENT device (the ABI layer has made the handle's device current), cached per device
 static int sm_count() {
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = cached[dev & 63];
+  if (!c) {
+    cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+    if (c <= 0) c = 148;
   }
-  return g_sm_count;
+  return c;
 }
 
 static int block_burst_pairs() {  // tuning knob of rm_march_block (RL_BLOCK_BURST_PAIRS), default RL_BLOCK_BURST / 2
@@ -1242,7 +1244,7 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     const int* perm = nullptr;
     const size_t struct_bytes = (KIND == RL_RM) ? m->dt_elems() * sizeof(float)
                                 : (KIND == RL_GLT) ? m->dt_elems() * (size_t)m->td * sizeof(uint16_t) : 0;
-    if (spatial && n >= 32768 && struct_bytes > ((size_t)48 << 20)) {
+    if (spatial && m->spatial_sort && n >= 32768 && struct_bytes > ((size_t)48 << 20)) {
       const int rc = spatial_order(m, ins, n, &perm);
       if (rc) return rc;
     }

@@ -185,6 +185,7 @@ struct rl_method {
 
   size_t dt_elems() const { return (size_t)W * H; }
   int coop_threshold = 8;
+  int spatial_sort = 1;  // big clouds on > L2 structures are processed in tile order (rl_sort.cu)
   int persist = 1;  // RM large batches: 0 one ray per thread, 1 persistent warps with lane re-queuing
   rl::MapView map_view() const {
     rl::MapView v{W, H, d_occ, d_bits_t, tiles8_y(), d_dt, coop_threshold, d_glt, td, 0.f, 0.f, 0.f, 0.f};

@@ -36,13 +36,15 @@ __global__ void patch_kernel(uint8_t* __restrict__ occ, const uint8_t* __restric
   occ[(size_t)(x0 + px) * H + (y0 + py)] = patch[idx] ? 1 : 0;
 }
 
-// ---- batched patches (dynamic maps, BASELINE config 4): one CTA per patch, two phases in one launch ----
+// ---- batched patches (dynamic maps, BASELINE config 4): one CTA per patch, two launches ----
 // rects[4*p .. 4*p+3] = x0, y0, w, h; patch p's bytes start at offsets[p] in `patches` (x-major inside the patch).
-// Patches of one batch must not share an 8x8 tile (block-aligned 16x16 patches never do) -- otherwise two CTAs
-// would rebuild the same tile word while one of them is still writing cells.
-__global__ void patch_batch_kernel(uint8_t* __restrict__ occ, unsigned long long* __restrict__ bits,
-                                   const uint8_t* __restrict__ patches, const int* __restrict__ rects,
-                                   const long long* __restrict__ offsets, int W, int H, int tiles_y) {
+// Phase 1 writes the cells of every patch; phase 2 (a second launch, so that ALL cells of the batch are in place)
+// rebuilds the 8x8-tile words each patch touches.  Patches that are not 8-aligned may share a tile: both CTAs then
+// rebuild the same word from the same, final cells -- identical stores, no ordering requirement.  (Round 1 did both
+// phases in one launch, which raced on shared tiles.)  Patches must still not overlap CELL-wise: which value an
+// overlapped cell ends up with would depend on the CTA schedule.
+__global__ void patch_batch_write_kernel(uint8_t* __restrict__ occ, const uint8_t* __restrict__ patches,
+                                         const int* __restrict__ rects, const long long* __restrict__ offsets, int H) {
   const int p = blockIdx.x;
   const int x0 = rects[4 * p], y0 = rects[4 * p + 1], w = rects[4 * p + 2], h = rects[4 * p + 3];
   const uint8_t* src = patches + offsets[p];
@@ -50,7 +52,12 @@ __global__ void patch_batch_kernel(uint8_t* __restrict__ occ, unsigned long long
     const int px = i / h, py = i - px * h;
     occ[(size_t)(x0 + px) * H + (y0 + py)] = src[i] ? 1 : 0;
   }
-  __syncthreads();
+}
+
+__global__ void patch_batch_pack_kernel(const uint8_t* __restrict__ occ, unsigned long long* __restrict__ bits,
+                                        const int* __restrict__ rects, int W, int H, int tiles_y) {
+  const int p = blockIdx.x;
+  const int x0 = rects[4 * p], y0 = rects[4 * p + 1], w = rects[4 * p + 2], h = rects[4 * p + 3];
   const int tx0 = x0 >> 3, tx1 = ((x0 + w - 1) >> 3) + 1, ty0 = y0 >> 3, ty1 = ((y0 + h - 1) >> 3) + 1;
   const int nty = ty1 - ty0;
   for (int t = threadIdx.x; t < (tx1 - tx0) * nty; t += blockDim.x) {
@@ -70,8 +77,10 @@ __global__ void patch_batch_kernel(uint8_t* __restrict__ occ, unsigned long long
 
 int apply_patch_batch(rl_method* m, const uint8_t* d_patches, const int* d_rects, const long long* d_offsets, int n) {
   if (n <= 0) return RL_OK;
-  patch_batch_kernel<<<n, 256, 0, m->stream>>>(m->d_occ, m->d_bits_t, d_patches, d_rects, d_offsets, m->W, m->H,
-                                               m->tiles8_y());
+  patch_batch_write_kernel<<<n, 256, 0, m->stream>>>(m->d_occ, d_patches, d_rects, d_offsets, m->H);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  patch_batch_pack_kernel<<<n, 64, 0, m->stream>>>(m->d_occ, m->d_bits_t, d_rects, m->W, m->H, m->tiles8_y());
   count_launch();
   RL_CHECK_LAUNCH();
   return RL_OK;

@@ -22,3 +22,20 @@ def load_png(path, threshold=128.0):
     if isinstance(path, bytes):
         path = path.decode()
     return occupancy_from_rgba(np.asarray(Image.open(path).convert("RGBA"), dtype=np.uint8), threshold)
+
+
+def save_png(path, occ_xmajor):
+    """OMap::save (RangeLib.h:264-291): RGBA8 image [rows = H][cols = W], (0,0,0,255) where grid[x][y] is set and
+    (255,255,255,255) elsewhere.  Returns False on success / True on error (the reference returns lodepng's code)."""
+    from PIL import Image
+    if isinstance(path, bytes):
+        path = path.decode()
+    occ = np.asarray(occ_xmajor)
+    img = np.full((occ.shape[1], occ.shape[0], 4), 255, np.uint8)
+    img[occ.T != 0, :3] = 0
+    try:
+        Image.fromarray(img, "RGBA").save(path, format="PNG")
+    except Exception as ex:  # noqa: BLE001
+        print("encoder error: %s" % ex)
+        return True
+    return False

@@ -2,12 +2,21 @@
 map / distance transform / sensor table replicated, per-particle weights gathered on every rank
 (SURVEY.md section 8e).  Plain ray batches need no collective; only the weights are exchanged.
 
-Two gather paths:
-  * "peer":  the fused kernel's epilogue stores each weight straight into every rank's gathered
-             array over NVLink (rl_calc_range_repeat_angles_eval_sensor_model_peers); the arrays
-             live in torch symmetric memory, and a symmetric-memory barrier orders the step.
-  * "nccl":  local fused kernel, then torch.distributed.all_gather_into_tensor (NCCL on GPUs;
-             gloo in the CPU tests, where the compute callable is injected).
+Gather paths:
+  * "peer":      the fused kernel's epilogue stores each weight straight into every rank's gathered
+                 array over NVLink (rl_calc_range_repeat_angles_eval_sensor_model_peers); the arrays
+                 live in torch symmetric memory, and a symmetric-memory barrier orders the step.
+  * "signalled": the same stores plus in-kernel epoch flags: one kernel per rank and step, no barrier launch.
+  * "host":      HostShardedSensorUpdate -- the signalled path behind ONE blocking call with host (numpy) buffers,
+                 rl_calc_range_repeat_angles_eval_sensor_model_sharded: what a multi-process particle filter
+                 written against the reference's Python API calls.
+  * "nccl":      local fused kernel, then torch.distributed.all_gather_into_tensor (NCCL on GPUs;
+                 gloo in the CPU tests, where the compute callable is injected).
+
+Streams: a method handle launches on its own private stream unless told otherwise.  Every GPU class here binds the
+handle to torch's CURRENT stream at each update() (method.set_stream), so the symmetric-memory barrier, the events
+and the consumer -- all on torch's current stream -- are ordered after the kernel's peer stores, and the kernel after
+whatever produced its inputs.
 The host-side logic here (slicing, gather bookkeeping, uneven shards) has no GPU dependency so that
 it can be exercised with world_size-2 gloo tests.
 """
@@ -67,9 +76,15 @@ class ShardedSensorUpdate:
         return self.weights_all
 
 
+def _bind_current_stream(method):
+    """Make the handle launch on torch's current stream (see the module docstring)."""
+    import torch
+    method.set_stream(torch.cuda.current_stream().cuda_stream)
+
+
 class PeerStoreSensorUpdate:
     """Fused compute + all-gather: the weights array lives in torch symmetric memory and the RM kernel
-    writes each rank's slice into every peer directly.  GPU only."""
+    writes each rank's slice into every peer directly.  GPU only.  update() runs on torch's current stream."""
 
     def __init__(self, n_total, method, angles, obs, group=None, device=None):
         import torch
@@ -87,22 +102,45 @@ class PeerStoreSensorUpdate:
         self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
 
     def update(self, local_particles):
+        _bind_current_stream(self.method)
         self.method.calc_range_repeat_angles_eval_sensor_model_peers(local_particles, self.angles, self.obs,
                                                                      self.peer_ptrs, self.lo)
         self.handle.barrier()  # every rank's stores have landed before anyone reads weights_all
         return self.weights_all
 
 
+def _signalled_buffers(n_total, method, group, device):
+    """Two gathered-weight buffers + one flag array in symmetric memory, registered with the handle."""
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bufs, handles = [], []
+    for _ in range(2):
+        t = symm_mem.empty(n_total, dtype=torch.float64, device=device)
+        bufs.append(t)
+        handles.append(symm_mem.rendezvous(t, group))
+    flags = symm_mem.empty(max(world, 2), dtype=torch.int64, device=device)
+    flags.zero_()
+    flag_handle = symm_mem.rendezvous(flags, group)
+    torch.cuda.synchronize()
+    flag_handle.barrier()  # every rank's flags are zero before anyone can signal
+    torch.cuda.synchronize()
+    method.peers_init([int(p) for p in handles[0].buffer_ptrs], [int(p) for p in handles[1].buffer_ptrs],
+                      [int(p) for p in flag_handle.buffer_ptrs], rank)
+    return bufs, handles, flags, flag_handle
+
+
 class SignalledSensorUpdate:
     """Fused compute + all-gather + synchronisation in ONE kernel per rank and step
     (rl_calc_range_repeat_angles_eval_sensor_model_signalled): weights are double buffered in symmetric
     memory, completion is signalled through peer-written epoch flags, and the only extra launch is the
-    consumer-side wait (update(..., wait=True)) before the gathered weights are read.  GPU only."""
+    consumer-side wait (update(..., wait=True)) before the gathered weights are read.  GPU only; runs on torch's
+    current stream.  The consumer of step k must be ordered before update() of step k+2 (same stream, or an event):
+    that launch overwrites the buffer it reads."""
 
     def __init__(self, n_total, method, angles, obs, group=None, device=None):
-        import torch
         import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
         self.dist = dist
         self.group = group or dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -110,34 +148,52 @@ class SignalledSensorUpdate:
         self.n_total = n_total
         self.lo, self.hi = particle_slice(n_total, self.rank, self.world)
         self.method, self.angles, self.obs = method, angles, obs
-        self.bufs, self.handles = [], []
-        for _ in range(2):
-            t = symm_mem.empty(n_total, dtype=torch.float64, device=device)
-            self.bufs.append(t)
-            self.handles.append(symm_mem.rendezvous(t, self.group))
-        self.flags = symm_mem.empty(max(self.world, 2), dtype=torch.int64, device=device)
-        self.flags.zero_()
-        self.flag_handle = symm_mem.rendezvous(self.flags, self.group)
-        torch.cuda.synchronize()
-        self.flag_handle.barrier()  # every rank's flags are zero before anyone can signal
-        torch.cuda.synchronize()
-        method.peers_init([int(p) for p in self.handles[0].buffer_ptrs], [int(p) for p in self.handles[1].buffer_ptrs],
-                          [int(p) for p in self.flag_handle.buffer_ptrs], self.rank)
+        _bind_current_stream(method)
+        self.bufs, self.handles, self.flags, self.flag_handle = _signalled_buffers(n_total, method, self.group, device)
 
     def update(self, local_particles, wait=True):
+        _bind_current_stream(self.method)
         b = self.method.calc_range_repeat_angles_eval_sensor_model_signalled(local_particles, self.angles, self.obs, self.lo)
         if wait:
             self.method.peers_wait()
         return self.bufs[b]
 
 
+class HostShardedSensorUpdate:
+    """The sharded update through HOST buffers in one blocking call per rank
+    (rl_calc_range_repeat_angles_eval_sensor_model_sharded): local particles in (numpy, ideally pinned), weights of
+    ALL particles out (numpy).  `method` may be the ctypes mirror (range_libc_b200.Py*) or the Cython drop-in
+    (range_libc.Py*): both expose peers_init and calc_range_repeat_angles_eval_sensor_model_sharded.  The handle keeps
+    its private stream; the call synchronises it before returning."""
+
+    def __init__(self, n_total, method, group=None, device=None):
+        import torch.distributed as dist
+        self.group = group or dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n_total = n_total
+        self.lo, self.hi = particle_slice(n_total, self.rank, self.world)
+        self.method = method
+        self.bufs, self.handles, self.flags, self.flag_handle = _signalled_buffers(n_total, method, self.group, device)
+
+    def update(self, local_particles, angles, obs, weights_all):
+        self.method.calc_range_repeat_angles_eval_sensor_model_sharded(local_particles, angles, obs, weights_all, self.lo)
+        return weights_all
+
+
 class PipelinedPeerStoreUpdate:
-    """PeerStoreSensorUpdate with the barrier of step k overlapped with the compute of step k+1: the gathered
-    weights are double buffered in symmetric memory, the fused kernel of step k stores into buffer k & 1 on the
-    main stream, and the symmetric-memory barrier that closes step k runs on a side stream while the kernel of
-    step k+1 is already computing.  Buffer k & 1 is reused by step k+2 only after its barrier has completed.
-    update() returns (buffer, event): the buffer holds the complete gather once the event has fired.
-    Throughput-oriented: the latency of one step is unchanged (kernel + barrier).  GPU only."""
+    """PeerStoreSensorUpdate with the barrier of step k overlapped with the compute of step k+1, for THROUGHPUT
+    workloads whose steps are independent (a particle filter that resamples on step k's weights before it can start
+    step k+1 gains nothing: use SignalledSensorUpdate / PeerStoreSensorUpdate).  The gathered weights are TRIPLE
+    buffered in symmetric memory; the fused kernel of step k stores into buffer k % 3 on the main stream, and the
+    symmetric-memory barrier that closes step k runs on a side stream while the kernel of step k+1 is computing.
+    Reuse rule: the kernel of step k may overwrite buffer k % 3 (last used by step k-3) once the barrier of step k-2
+    has completed -- every rank has then launched its step k-2, so, PROVIDED each rank's consumer of step j is ordered
+    before its update() of step j+1 (same stream, or an event the main stream waits on), every consumer of step k-3
+    has finished.  update() returns (buffer, event): the buffer holds the complete gather once the event has fired.
+    GPU only; the main stream is torch's current stream."""
+
+    NBUF = 3
 
     def __init__(self, n_total, method, angles, obs, group=None, device=None):
         import torch
@@ -151,22 +207,25 @@ class PipelinedPeerStoreUpdate:
         self.lo, self.hi = particle_slice(n_total, self.rank, self.world)
         self.method, self.angles, self.obs = method, angles, obs
         self.bufs, self.handles, self.ptrs = [], [], []
-        for _ in range(2):
+        for _ in range(self.NBUF):
             t = symm_mem.empty(n_total, dtype=torch.float64, device=device)
             h = symm_mem.rendezvous(t, self.group)
             self.bufs.append(t)
             self.handles.append(h)
             self.ptrs.append([int(p) for p in h.buffer_ptrs])
         self.side = torch.cuda.Stream(device=device)
-        self.done = [None, None]  # event: barrier of the last step that used buffer b has completed
+        self.done = {}  # step -> event: the barrier closing that step has completed
         self.k = 0
 
     def update(self, local_particles):
         torch = self.torch
         main = torch.cuda.current_stream()
-        b = self.k & 1
-        if self.done[b] is not None:
-            main.wait_event(self.done[b])
+        _bind_current_stream(self.method)
+        k = self.k
+        b = k % self.NBUF
+        if k - 2 in self.done:
+            main.wait_event(self.done[k - 2])
+        self.done.pop(k - 3, None)
         self.method.calc_range_repeat_angles_eval_sensor_model_peers(local_particles, self.angles, self.obs,
                                                                      self.ptrs[b], self.lo)
         ready = torch.cuda.Event()
@@ -176,7 +235,7 @@ class PipelinedPeerStoreUpdate:
             self.handles[b].barrier()
             ev = torch.cuda.Event()
             ev.record(self.side)
-        self.done[b] = ev
+        self.done[k] = ev
         self.k += 1
         return self.bufs[b], ev
 
@@ -184,12 +243,11 @@ class PipelinedPeerStoreUpdate:
         """forget the events of earlier steps.  Call only when all earlier work has completed on every rank (e.g.
         after a device synchronise + process-group barrier), and around CUDA-graph capture: a capturing stream
         must not wait on events recorded outside the capture, nor eager work on events recorded inside it."""
-        self.done = [None, None]
+        self.done = {}
         self.k = 0
 
     def finish(self):
         """join the side stream: every gather issued so far is complete once the main stream gets here"""
         main = self.torch.cuda.current_stream()
-        for ev in self.done:
-            if ev is not None:
-                main.wait_event(ev)
+        for ev in self.done.values():
+            main.wait_event(ev)

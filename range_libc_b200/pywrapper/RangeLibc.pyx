@@ -40,6 +40,7 @@ cdef extern from "rangelib_b200.h":
     int rl_map_create(const uint8_t* occ, int w, int h, rl_map** out)
     int rl_map_set_world(rl_map* m, float scale, float angle, float ox, float oy, float s, float c)
     int rl_map_is_occupied(const rl_map* m, int x, int y)
+    int rl_map_get(const rl_map* m, uint8_t* out)
     void rl_map_destroy(rl_map* m)
     int rl_method_create(int kind, const rl_map* m, float max_range, unsigned td, int device, rl_method** out)
     void rl_method_destroy(rl_method* m)
@@ -54,6 +55,10 @@ cdef extern from "rangelib_b200.h":
                                                       const float* obs, double* weights, int n, int k)
     int rl_calc_range_many_radial_optimized(rl_method* m, const float* ins, float* outs, int n, int num_rays,
                                             float min_angle, float max_angle)
+    int rl_method_peers_init(rl_method* m, double** w0, double** w1, int64_t** flags, int n_peers, int rank)
+    int rl_calc_range_repeat_angles_eval_sensor_model_sharded(rl_method* m, const float* ins, const float* angles,
+                                                              const float* obs, double* weights_all, int64_t offset,
+                                                              int n, int k, int64_t n_total)
 
 # the reference exports its compile-time switches; keep the names importable
 USE_CACHED_TRIG = False
@@ -87,9 +92,13 @@ def _decode_png(path, threshold):
     from PIL import Image
     if isinstance(path, bytes):
         path = path.decode()
-    img = np.asarray(Image.open(path).convert("RGBA"), dtype=np.float32)
-    gray = (0.229 * img[:, :, 2].astype(np.float64) + 0.587 * img[:, :, 1] + 0.114 * img[:, :, 0]).astype(np.float32)
-    gray = gray.astype(np.int32)
+    img = np.asarray(Image.open(path).convert("RGBA"), dtype=np.uint8)
+    # all three products and both sums in double, narrowed to float on return and truncated (RangeUtils.h:30-32),
+    # exactly as range_libc_b200.mapio.occupancy_from_rgba and the device ingest kernel do
+    r = img[:, :, 2].astype(np.float64)
+    g = img[:, :, 1].astype(np.float64)
+    b = img[:, :, 0].astype(np.float64)
+    gray = ((0.229 * r + 0.587 * g) + 0.114 * b).astype(np.float32).astype(np.int32)
     return np.ascontiguousarray((gray < threshold).T, dtype=np.uint8)
 
 
@@ -152,7 +161,22 @@ cdef class PyOMap:
         return self._h
 
     def save(self, fn):
-        raise NotImplementedError("PNG writing is outside the accelerated path")
+        """OMap::save (RangeLib.h:264-291): RGBA PNG, occupied cells black, free cells white, alpha 255.
+        Returns False on success like the reference (its return value is lodepng's error code)."""
+        from PIL import Image
+        np_occ = np.empty((self._w, self._h), np.uint8)
+        cdef uint8_t[:, ::1] view = np_occ
+        _ck(rl_map_get(self.ptr, &view[0, 0]))
+        img = np.full((self._h, self._w, 4), 255, np.uint8)
+        img[np_occ.T != 0, :3] = 0
+        if isinstance(fn, bytes):
+            fn = fn.decode()
+        try:
+            Image.fromarray(img, "RGBA").save(fn, format="PNG")
+        except Exception as ex:
+            print("encoder error: %s" % ex)
+            return True
+        return False
 
 
 cdef class _Method:
@@ -195,6 +219,34 @@ cdef class _Method:
             raise ValueError("shape mismatch")
         _ck(rl_calc_range_repeat_angles_eval_sensor_model(self.ptr, &ins[0, 0], &angles[0], &obs[0], &weights[0],
                                                           <int>ins.shape[0], <int>angles.shape[0]))
+
+    def peers_init(self, weights0_ptrs, weights1_ptrs, flags_ptrs, int rank):
+        """Multi-process extension (no counterpart in the single-GPU reference): peer-mapped device pointers of every
+        rank's two gathered-weight buffers and flag array (e.g. torch symmetric memory; see range_libc_b200.parallel)."""
+        cdef double* w0[16]
+        cdef double* w1[16]
+        cdef int64_t* fl[16]
+        cdef int n = len(weights0_ptrs)
+        if n < 1 or n > 16 or len(weights1_ptrs) != n or len(flags_ptrs) != n:
+            raise ValueError("1..16 peers, three pointer lists of equal length")
+        for i in range(n):
+            w0[i] = <double*><size_t>int(weights0_ptrs[i])
+            w1[i] = <double*><size_t>int(weights1_ptrs[i])
+            fl[i] = <int64_t*><size_t>int(flags_ptrs[i])
+        _ck(rl_method_peers_init(self.ptr, w0, w1, fl, n, rank))
+
+    cpdef calc_range_repeat_angles_eval_sensor_model_sharded(self, float[:, ::1] ins, float[::1] angles, float[::1] obs,
+                                                             double[::1] weights_all, long long offset):
+        """calc_range_repeat_angles_eval_sensor_model for a cloud sharded over several processes / GPUs: `ins` are
+        THIS rank's particles (starting at particle `offset` of the cloud), `weights_all` receives the weights of ALL
+        particles (gathered over NVLink by the kernel's epilogue).  Blocking; needs peers_init."""
+        if ins.shape[0] == 0 or angles.shape[0] == 0:
+            raise ValueError("every rank must pass at least one particle and one angle")
+        if ins.shape[1] != 3 or obs.shape[0] < angles.shape[0] or weights_all.shape[0] < offset + ins.shape[0]:
+            raise ValueError("shape mismatch")
+        _ck(rl_calc_range_repeat_angles_eval_sensor_model_sharded(self.ptr, &ins[0, 0], &angles[0], &obs[0],
+                                                                  &weights_all[0], offset, <int>ins.shape[0],
+                                                                  <int>angles.shape[0], <int64_t>weights_all.shape[0]))
 
     cpdef calc_range_many_radial_optimized(self, int num_rays, float min_angle, float max_angle, float[:, ::1] ins,
                                            float[::1] outs):

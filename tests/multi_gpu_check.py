@@ -87,8 +87,33 @@ def main():
         results["pipelined"] = ok_all
     except Exception as ex:  # noqa: BLE001
         results["pipelined"] = "unavailable: %s" % str(ex).splitlines()[0]
+    # the sharded update through HOST buffers (one blocking call per rank), both bindings; 1080 beams: the
+    # one-particle-per-CTA shape of BASELINE config 5
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "range_libc_b200", "pywrapper"))
+        import range_libc as cy
+        for label, mod, m_beams in (("host_ctypes", rl, M), ("host_cython", cy, M), ("host_cython_1080", cy, 1080)):
+            cmap = mod.PyOMap(np.ascontiguousarray(occ.T.astype(bool)))
+            meth = mod.PyRayMarchingGPU(cmap, 500.0)
+            meth.set_sensor_model(table)
+            n_sub = n_total if m_beams == M else 301
+            a_h = wl.lidar_angles(m_beams)
+            o_h = np.linspace(10, 400, m_beams).astype(np.float32)
+            host = parallel.HostShardedSensorUpdate(n_sub, meth, device=dev)
+            ok_all = True
+            for it in range(3):  # three epochs: both buffers, flag reuse
+                pts = particles[:n_sub].copy()
+                pts[:, 0] += 0.25 * it
+                w_all = np.zeros(n_sub, np.float64)
+                host.update(np.ascontiguousarray(pts[host.lo:host.hi]), a_h, o_h, w_all)
+                ref_it = ora.calc_range_repeat_angles_eval_sensor_model(pts, a_h, o_h)
+                ok_all &= bool(np.array_equal(w_all.view(np.uint64), ref_it.view(np.uint64)))
+            results[label] = ok_all
+            dist.barrier()
+    except Exception as ex:  # noqa: BLE001
+        results["host"] = "FAILED: %s" % str(ex).splitlines()[0]
     print("rank %d/%d: %s" % (rank, world, results), flush=True)
-    ok = results["nccl"] is True and all(results[k] is True or isinstance(results[k], str) for k in ("peer", "signalled", "pipelined"))
+    ok = results["nccl"] is True and all(v is True or (isinstance(v, str) and v.startswith("unavailable")) for v in results.values())
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

