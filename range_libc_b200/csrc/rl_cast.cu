@@ -42,11 +42,19 @@ __device__ __forceinline__ void rl_trace_mark(int slot) {
 __device__ __forceinline__ void rl_trace_value(int slot, unsigned long long v) {
   if (g_rl_trace && threadIdx.x == 0) g_rl_trace[(size_t)blockIdx.x * 16 + slot] = v;
 }
+__device__ __forceinline__ void rl_trace_add(int slot, unsigned long long v) {  // any thread
+  if (g_rl_trace) atomicAdd(&g_rl_trace[(size_t)blockIdx.x * 16 + slot], v);
+}
 #define RL_TRACE_MARK(slot) rl_trace_mark(slot)
 #define RL_TRACE_VALUE(slot, v) rl_trace_value(slot, (unsigned long long)(v))
+#define RL_TRACE_ADD(slot, v) rl_trace_add(slot, (unsigned long long)(v))
+__device__ __forceinline__ void rl_trace_max(int slot, unsigned long long v) {  // any thread
+  if (g_rl_trace) atomicMax(&g_rl_trace[(size_t)blockIdx.x * 16 + slot], v);
+}
 #else
 #define RL_TRACE_MARK(slot)
 #define RL_TRACE_VALUE(slot, v)
+#define RL_TRACE_ADD(slot, v)
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -98,56 +106,178 @@ __device__ __forceinline__ bool rm_step(const MapView& mv, float max_range, floa
 #ifndef RL_COOP_PROBES
 #define RL_COOP_PROBES 2  // probes per lane and batch: 64 probes = 48 px of ray per L2 round trip
 #endif
+#ifndef RL_COOP_UNROLL
+#define RL_COOP_UNROLL 2  // replay steps per exit test (2: 21.0 us, 4: 21.3, 8: 22.4 per 4000 x 60 update)
+#endif
 #define RL_STEP_INF 0x7f800000u  // +inf in the per-lane step table: "obstacle here" -- and the value of "no probe"
+
+// Conservative parameter interval of one probed cell (round 2).  The replay loop of rm_march_coop has to know, for the
+// current parameter t, which probed cell the reference's sample (int)(x0 + dx t), (int)(y0 + dy t) falls into.  Round 1
+// recomputed that cell on every replay step (FMUL, FADD, F2I, key build, compare: half of a ~100-cycle dependent chain,
+// tools/replay_bench.cu).  A cell is a parameter INTERVAL of the ray, so each lane can instead carry [lo, hi] for its
+// probe and the replay step becomes two compares, a select and the warp-wide minimum (46 cycles measured).  Exactness:
+// the interval is made a SUBSET of the cell's true float preimage --
+//   fl(x0 + fl(dx t)) differs from the real number X(t) = x0 + dx t by at most E0 = 2^-24 (|dx t| + |X|) <=
+//   2^-24 (max_range + side + 1); a parameter with X(t) in [cx + margin, cx + 1 - margin], margin = 8 E0, therefore
+//   truncates to cx (for cx = 0 the reference's cell also covers (-1, 0); not claiming that part is conservative).
+//   The interval ends are formed with three float operations each; their rounding (relative 2^-23 of the end, plus
+//   2^-23 side in X, well inside the margin) is covered by moving the ends inwards by a relative 2^-20 --
+// and a parameter no lane claims (a margin zone, a clipped corner, a jump past the window, the map edge) simply takes the
+// exact round-1 test.  The claim therefore never decides differently from the exact computation; it only skips it.
+struct CoopRay {
+  float x0, y0, dx, dy, inv_dx, inv_dy, margin;
+  float below_max;  // the largest float below max_range: no interval claims a parameter the reference's loop never samples
+};
+
+__device__ __forceinline__ CoopRay coop_ray(const MapView& mv, float max_range, float x0, float y0, float dx, float dy) {
+  CoopRay r;
+  r.x0 = x0; r.y0 = y0; r.dx = dx; r.dy = dy;
+  r.inv_dx = __fdiv_rn(1.0f, dx);
+  r.inv_dy = __fdiv_rn(1.0f, dy);
+  r.below_max = nextafterf(max_range, -INFINITY);
+  r.margin = fmul(4.76837158203125e-07f /* 2^-21 */, fadd(fadd(max_range, (float)max(mv.W, mv.H)), 2.0f));
+  return r;
+}
+
+// [lo, hi] for one axis: parameters whose coordinate lies in [c + margin, c + 1 - margin]
+__device__ __forceinline__ void coop_axis_interval(float c, float o, float d, float inv_d, float margin, float* lo,
+                                                   float* hi) {
+  const float a = fsub(c, o);                        // c - x0
+  const float near = fmul(fadd(a, margin), inv_d);   // parameter of the edge at c (+ margin)
+  const float far = fmul(fsub(fadd(a, 1.0f), margin), inv_d);  // parameter of the edge at c + 1 (- margin)
+  if (d > 0.0f) { *lo = near; *hi = far; }
+  else if (d < 0.0f) { *lo = far; *hi = near; }
+  else { *lo = -INFINITY; *hi = INFINITY; }          // the coordinate never changes: fl(o + fl(0 t)) == o
+}
+
 __device__ __forceinline__ float rm_march_coop(const MapView& mv, float max_range, float x0, float y0, float dx,
                                                float dy, float t) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned W = (unsigned)mv.W, H = (unsigned)mv.H;
+  const CoopRay cr = coop_ray(mv, max_range, x0, y0, dx, dy);
+#ifdef RL_TRACE
+  unsigned n_batches = 0, n_fast = 0, n_exact = 0, n_groups = 0;
+  long long c_replay = 0, c_mark = 0;
+  const long long c_enter = clock64();
+#define RL_COOP_COUNT(x) (++(x))
+#define RL_COOP_CLOCK_BEGIN() (c_mark = clock64())
+#define RL_COOP_CLOCK_END() (c_replay += clock64() - c_mark)
+  // slots 11-13: totals over the CTA's rays; 14 / 15: the CTA's longest single ray -- cycles in the tail packed with
+  // its cycles inside replay loops (<< 32), and its steps packed with its batches (<< 32)
+#define RL_COOP_REPORT()                                                                                   \
+  do {                                                                                                     \
+    if (lane == 0) {                                                                                       \
+      RL_TRACE_ADD(11, n_batches);                                                                         \
+      RL_TRACE_ADD(12, n_fast + n_groups * RL_COOP_UNROLL);                                                                            \
+      RL_TRACE_ADD(13, n_exact);                                                                           \
+      rl_trace_max(14, ((unsigned long long)(clock64() - c_enter) << 32) | (unsigned)c_replay);            \
+      rl_trace_max(15, ((unsigned long long)(n_fast + n_groups * RL_COOP_UNROLL) << 32) | n_batches);                                    \
+    }                                                                                                      \
+  } while (0)
+#else
+#define RL_COOP_COUNT(x)
+#define RL_COOP_CLOCK_BEGIN()
+#define RL_COOP_CLOCK_END()
+#define RL_COOP_REPORT()
+#endif
   while (true) {
+    RL_COOP_COUNT(n_batches);
     // ---- probe batch: probe p of lane j reads the cell at parameter t + 0.75 (32 p + j) and keeps the
     // step that cell implies.  The loads of a lane are independent (one L2 round trip for the batch).
     // Cells are identified by key = cx << 16 | cy; this path is only taken when W, H and max_range are
     // below 32768, so a sample outside the map (coordinate negative or >= the side) can never produce
-    // the key of a probed cell; unused probes carry key -1 and a step of +inf.
+    // the key of a probed cell; unused probes carry key -1, a step of +inf and an empty interval.
     int key[RL_COOP_PROBES];
     unsigned stepbits[RL_COOP_PROBES];
+    float lo[RL_COOP_PROBES], hi[RL_COOP_PROBES];
+    // Branch-free, in three sweeps, so that all loads of the batch are in flight together: a probe outside the
+    // map reads cell 0 and is discarded (a branch around the load made ptxas serialise the two probes of a lane:
+    // two L2 round trips per batch, measured +2.3 us on the 4000 x 60 update).
+    float d[RL_COOP_PROBES];
+    bool inb[RL_COOP_PROBES];
+    int cxs[RL_COOP_PROBES], cys[RL_COOP_PROBES];
 #pragma unroll
     for (int p = 0; p < RL_COOP_PROBES; ++p) {
       const float s = t + (float)(32 * p + lane) * RL_COOP_SPACING;  // p = 0, lane 0: exactly t
-      const int cx = __float2int_rz(fadd(x0, fmul(dx, s)));
-      const int cy = __float2int_rz(fadd(y0, fmul(dy, s)));
-      key[p] = -1;
-      stepbits[p] = RL_STEP_INF;
-      if ((unsigned)cx < W && (unsigned)cy < H) {
-        key[p] = (cx << 16) | cy;
-        const float d = __ldg(mv.dt + dt_index(cx, cy, mv.H));
-        stepbits[p] = (d <= 0.0f) ? RL_STEP_INF : __float_as_uint(fmaxf(fmul(d, 0.999f), 1.0f));
-      }
+      cxs[p] = __float2int_rz(fadd(x0, fmul(dx, s)));
+      cys[p] = __float2int_rz(fadd(y0, fmul(dy, s)));
+      inb[p] = (unsigned)cxs[p] < W && (unsigned)cys[p] < H;
+      d[p] = __ldg(mv.dt + (inb[p] ? dt_index(cxs[p], cys[p], mv.H) : 0u));
     }
+#pragma unroll
+    for (int p = 0; p < RL_COOP_PROBES; ++p) {
+      float lx, hx, ly, hy;
+      coop_axis_interval((float)cxs[p], x0, dx, cr.inv_dx, cr.margin, &lx, &hx);
+      coop_axis_interval((float)cys[p], y0, dy, cr.inv_dy, cr.margin, &ly, &hy);
+      // inwards by a relative 2^-20 (t >= 0: a lower end below 0 is 0)
+      lo[p] = inb[p] ? fmul(fmaxf(fmaxf(lx, ly), 0.0f), 1.00000095367431640625f) : INFINITY;
+      hi[p] = inb[p] ? fminf(fmul(fminf(hx, hy), 0.99999904632568359375f), cr.below_max) : -INFINITY;
+      key[p] = inb[p] ? ((cxs[p] << 16) | cys[p]) : -1;
+    }
+#pragma unroll
+    for (int p = 0; p < RL_COOP_PROBES; ++p)
+      stepbits[p] = (inb[p] && !(d[p] <= 0.0f)) ? __float_as_uint(fmaxf(fmul(d[p], 0.999f), 1.0f)) : RL_STEP_INF;
     // ---- replay the reference's steps out of the probes: one warp-wide min-reduction per step.
-    // A lane offers the step of its probe if the probe is the sampled cell, +inf otherwise; +inf
-    // (obstacle, cell not probed, or sample outside the map) ends the loop through its only exit
-    // test and the three cases are told apart afterwards.
+    // A lane offers the step of its probe if the sample is certainly in the probe's cell (interval test), +inf
+    // otherwise.  +inf from that reduction (obstacle, nobody sure) takes the exact test: a lane offers its step if
+    // the probe IS the sampled cell.  +inf from the exact test (obstacle, cell not probed, or sample outside the
+    // map) ends the loop through its only exit test and the three cases are told apart afterwards.
     float tp;
-    int k0, px, py;
-    do {
-      tp = t;
-      px = __float2int_rz(fadd(x0, fmul(dx, t)));
-      py = __float2int_rz(fadd(y0, fmul(dy, t)));
-      k0 = (px << 16) | py;
+    RL_COOP_CLOCK_BEGIN();
+    while (true) {
+      // fast loop: RL_COOP_UNROLL steps of straight-line code per exit test (measured in place, round 2: of the
+      // ~105 cycles of a replay step ~25 were the `claimed?` branch and ~25 the loop branch).  No interval reaches
+      // max_range (hi is clamped below it), so the first parameter that is not `< max_range` -- a real step past
+      // max_range, or +inf because nobody claimed the sample -- turns every later one into +inf: the parameters of
+      // a group form a valid prefix followed by the stop, which is picked out afterwards.
+      float ts[RL_COOP_UNROLL + 1];
+      do {
+        ts[0] = t;
+#pragma unroll
+        for (int u = 0; u < RL_COOP_UNROLL; ++u) {
+          const float tu = ts[u];
+          unsigned mine = (tu >= lo[0] && tu <= hi[0]) ? stepbits[0] : RL_STEP_INF;
+#pragma unroll
+          for (int p = 1; p < RL_COOP_PROBES; ++p) mine = (tu >= lo[p] && tu <= hi[p]) ? stepbits[p] : mine;
+          ts[u + 1] = fadd(tu, __uint_as_float(__reduce_min_sync(FULL, mine)));
+        }
+        t = ts[RL_COOP_UNROLL];
+        RL_COOP_COUNT(n_groups);
+      } while (t < max_range);
+      tp = ts[0];
+      t = ts[1];
+#pragma unroll
+      for (int u = 1; u < RL_COOP_UNROLL; ++u) {
+        if (ts[u] < max_range) {
+          tp = ts[u];
+          t = ts[u + 1];
+        }
+      }
+      if (t != __uint_as_float(RL_STEP_INF)) break;  // a real step carried t to max_range
+      // nobody was sure about the sample at tp: the exact test
+      RL_COOP_COUNT(n_exact);
+      const int ex = __float2int_rz(fadd(x0, fmul(dx, tp)));
+      const int ey = __float2int_rz(fadd(y0, fmul(dy, tp)));
+      const int k0 = (ex << 16) | ey;
       unsigned mine = (key[0] == k0) ? stepbits[0] : RL_STEP_INF;
 #pragma unroll
       for (int p = 1; p < RL_COOP_PROBES; ++p) mine = (key[p] == k0) ? stepbits[p] : mine;
-      t = fadd(t, __uint_as_float(__reduce_min_sync(FULL, mine)));
-    } while (t < max_range);
-    if ((unsigned)px >= W || (unsigned)py >= H) return max_range;  // left the map (RangeLib.h:942-944)
-    if (t != __uint_as_float(RL_STEP_INF)) return max_range;       // a real step carried t to max_range (:938)
+      t = fadd(tp, __uint_as_float(__reduce_min_sync(FULL, mine)));
+      if (!(t < max_range)) break;  // +inf (obstacle, cell not probed, outside the map) or max_range reached
+    }
+    RL_COOP_CLOCK_END();
+    const int px = __float2int_rz(fadd(x0, fmul(dx, tp)));
+    const int py = __float2int_rz(fadd(y0, fmul(dy, tp)));
+    if ((unsigned)px >= W || (unsigned)py >= H) { RL_COOP_REPORT(); return max_range; }  // left the map (RangeLib.h:942-944)
+    if (t != __uint_as_float(RL_STEP_INF)) { RL_COOP_REPORT(); return max_range; }  // a real step carried t to max_range (:938)
+    const int k0 = (px << 16) | py;
     bool probed = false;
 #pragma unroll
     for (int p = 0; p < RL_COOP_PROBES; ++p) probed = probed || key[p] == k0;
     if (__any_sync(FULL, probed)) {  // probed and +inf: d <= distThreshold (:952-956)
       const float xd = fsub((float)px, x0), yd = fsub((float)py, y0);
+      RL_COOP_REPORT();
       return __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
     }
     t = tp;  // cell not probed: next batch starts at this sample
@@ -699,6 +829,52 @@ radial_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const flo
       row[a] = fmul(cast_one<KIND>(mv, cv, max_range, y, x, th), xf.scale);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// CDDT / PCDDT on tables larger than L2 (BASELINE config 3: gigantic_map, 636 MB of zero points, 235 MB pruned).
+// A query reads two offsets, the ends of its bin and ~log2(bin size) probes of a binary search.  With the queries
+// in caller order every one of those reads is its own DRAM sector (ncu, round 2: 534 B of DRAM traffic per query,
+// L2 hit rate 20 %, 8.4 G rays/s).  The bin a query lands in is cheap to compute (theta -> slice, one rotation), so
+// large batches are first ORDERED BY BIN: a key kernel writes (bin, ray index), a radix sort over the significant
+// key bits orders the pairs, and the cast kernel walks the sorted pairs -- the lanes of a warp then search the
+// same or neighbouring bins, their probes share lines (the upper levels of the search are the same address for
+// the whole warp), and the table streams through L2 once.  Each result is computed by cddt_cast as before and
+// stored at its ray's own index.
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+cddt_key_kernel(CddtView cv, WorldXform xf, const float* __restrict__ ins, const float* __restrict__ angles,
+                long long total, int M, unsigned sentinel, unsigned* __restrict__ keys, int* __restrict__ idx) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= total) return;
+  float x, y, th;
+  load_pose<MODE>(xf, ins, angles, r, M, &x, &y, &th);
+  unsigned key = sentinel;  // rays that never reach a bin (non-finite pose, rotated y outside the slice)
+  if (finite3(x, y, th)) {
+    int a;
+    bool flipped;
+    cddt_discretize(cv, -th, &a, &flipped);
+    const float ly = fadd(fadd(fmul(x, __ldg(cv.sinv + a)), fmul(y, __ldg(cv.cosv + a))), __ldg(cv.trans + a));
+    const unsigned li = (unsigned)f2i(ly);
+    if (li < (unsigned)__ldg(cv.widths + a)) key = (unsigned)(__ldg(cv.slice0 + a) + li);
+  }
+  keys[r] = key;
+  idx[r] = (int)r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+cddt_sorted_cast_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float* __restrict__ ins,
+                        const float* __restrict__ angles, float* __restrict__ outs, const int* __restrict__ perm,
+                        long long total, int M) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long r = __ldg(perm + i);
+  float x, y, th;
+  load_pose<MODE>(xf, ins, angles, r, M, &x, &y, &th);
+  const float range = cddt_cast(mv, cv, max_range, x, y, th);
+  outs[r] = (MODE == MODE_GRID) ? range : fmul(range, xf.scale);
 }
 
 // One CTA handles `ppb` consecutive particles per iteration (grid-stride over particle groups).
@@ -1269,6 +1445,41 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     }
   } else {
     const long long total = (mode == MODE_ANGLES) ? (long long)n * M : (long long)n;
+    // CDDT / PCDDT, big batch on a table larger than L2: bin-ordered processing (see cddt_key_kernel)
+    static const bool cddt_sort = !(getenv("RL_CDDT_SORT") && atoi(getenv("RL_CDDT_SORT")) == 0);
+    if (KIND == RL_CDDT && cddt_sort && m->spatial_sort && total >= (1LL << 18) && total < (1LL << 31) &&
+        (size_t)m->nvalues * sizeof(float) > ((size_t)48 << 20) && m->nbins < (int64_t)0xfffffff0u) {
+      unsigned* keys = nullptr;
+      int* idx = nullptr;
+      int rc = sort_buffers(m, (int)total, &keys, &idx);
+      if (rc) return rc;
+      const unsigned sentinel = (unsigned)m->nbins;
+      const unsigned kgrid = (unsigned)((total + 255) / 256);
+      if (mode == MODE_GRID)
+        cddt_key_kernel<MODE_GRID><<<kgrid, 256, 0, m->stream>>>(cv, m->xf, ins, angles, total, M, sentinel, keys, idx);
+      else if (mode == MODE_WORLD)
+        cddt_key_kernel<MODE_WORLD><<<kgrid, 256, 0, m->stream>>>(cv, m->xf, ins, angles, total, M, sentinel, keys, idx);
+      else
+        cddt_key_kernel<MODE_ANGLES><<<kgrid, 256, 0, m->stream>>>(cv, m->xf, ins, angles, total, M, sentinel, keys, idx);
+      count_launch();
+      RL_CHECK_LAUNCH();
+      int bits = 1;
+      while (bits < 32 && (1ull << bits) <= (unsigned long long)sentinel) ++bits;
+      // the top 16 key bits are enough: what matters is that a warp's bins are neighbours, not their exact order
+      static const int sort_bits = getenv("RL_CDDT_SORT_BITS") ? max(1, atoi(getenv("RL_CDDT_SORT_BITS"))) : 16;
+      const int* perm = nullptr;
+      rc = sort_pairs(m, (int)total, max(0, bits - sort_bits), bits, &perm);
+      if (rc) return rc;
+      if (mode == MODE_GRID)
+        cddt_sorted_cast_kernel<MODE_GRID><<<kgrid, 256, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, perm, total, M);
+      else if (mode == MODE_WORLD)
+        cddt_sorted_cast_kernel<MODE_WORLD><<<kgrid, 256, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, perm, total, M);
+      else
+        cddt_sorted_cast_kernel<MODE_ANGLES><<<kgrid, 256, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, perm, total, M);
+      count_launch();
+      RL_CHECK_LAUNCH();
+      return RL_OK;
+    }
     // RM with enough rays to give every resident warp more than one ray per lane: persistent
     // warps with lane re-queuing.  (max_range <= 0 never enters the marching loop.)
     if (KIND == RL_BL && total >= (long long)sm_count() * 40 * 64 && m->persist) {

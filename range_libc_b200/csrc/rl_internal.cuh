@@ -218,6 +218,8 @@ int cddt_prune(rl_method* m, float max_range);
 void cddt_free(rl_method* m);
 // rl_sort.cu
 int spatial_order(rl_method* m, const float* d_ins, int n, const int** d_perm);
+int sort_buffers(rl_method* m, int n, unsigned** d_keys, int** d_idx);
+int sort_pairs(rl_method* m, int n, int begin_bit, int end_bit, const int** d_perm);
 void sort_free(rl_method* m);
 // rl_cast.cu -- the batched query kernels (all kinds, all modes)
 int launch_cast(rl_method* m, int mode, const float* d_ins, const float* d_angles, const float* d_obs, float* d_outs,

@@ -199,3 +199,56 @@ def test_multi_gpu_torchrun_all_gather_paths():
                         os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, env=env,
                        timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+@pytest.mark.parametrize("name,pruned", [("gigantic_map", False), ("huge_map", True)])
+def test_c3_bin_ordered_cddt_queries(name, pruned):
+    """C3: big CDDT / PCDDT batches on tables larger than L2 are processed in bin order (key kernel + radix sort +
+    sorted cast).  Only the processing order changes: the first 20 000 results reproduce the reference digests, the
+    whole batch equals a launch in caller order, in grid, world and repeat-angles form."""
+    import json
+    import torch
+    from helpers import GOLD
+    dig = json.load(open(os.path.join(GOLD, "big_digests.json")))[name]
+    occ = wl.load_map(name)
+    W, H = occ.shape
+    omap = omap_of(occ)
+    world = (0.05, 0.3, -3.0, 2.0, float(np.float32(np.sin(0.3))), float(np.float32(np.cos(0.3))))
+    omap.set_world(*world)
+    cd = rl.PyCDDTCast(omap, MR, TD)
+    if pruned:
+        cd.prune()
+    q = np.concatenate([wl.random_queries(W, H, 20000, seed=777), wl.random_queries(W, H, (1 << 20) - 20000, seed=778)])
+    q[30000] = [np.nan, 5.0, 1.0]          # rays that reach no bin sort to the end and still get max_range
+    q[30001] = [-1e9, 3e9, 0.5]
+    qd = torch.from_numpy(q).cuda()
+    out = torch.empty(len(q), dtype=torch.float32, device="cuda")
+    l0 = rl.kernel_launches()
+    cd.calc_range_many_grid(qd, out)
+    cd.synchronize()
+    assert rl.kernel_launches() - l0 >= 4, "the bin-ordered path did not run"
+    got = out.cpu().numpy()
+    key = "pcddt_ranges_sha256" if pruned else "cddt_ranges_sha256"
+    assert hashlib.sha256(got[:20000].tobytes()).hexdigest() == dig[key]
+    assert got[30000] == MR and got[30001] == MR
+    cd.set_spatial_sort(False)
+    out2 = torch.empty_like(out)
+    l0 = rl.kernel_launches()
+    cd.calc_range_many_grid(qd, out2)
+    cd.synchronize()
+    assert rl.kernel_launches() - l0 == 1
+    assert_bit_equal(got, out2.cpu().numpy(), "%s bin-ordered vs caller-ordered, grid" % name)
+    # world-frame batch and lidar fans
+    qw = torch.from_numpy(wl.grid_to_world(q[:1 << 19], world[0], world[2], world[3], world[1])).cuda()
+    angles = torch.from_numpy(wl.lidar_angles(16)).cuda()
+    res = {}
+    for sort in (True, False):
+        cd.set_spatial_sort(sort)
+        a = torch.empty(len(qw), dtype=torch.float32, device="cuda")
+        b = torch.empty(32768 * 16, dtype=torch.float32, device="cuda")
+        cd.calc_range_many(qw, a)
+        cd.calc_range_repeat_angles(qw[:32768].contiguous(), angles, b)
+        cd.synchronize()
+        res[sort] = (a.cpu().numpy(), b.cpu().numpy())
+    assert_bit_equal(res[True][0], res[False][0], "%s bin-ordered vs caller-ordered, world" % name)
+    assert_bit_equal(res[True][1], res[False][1], "%s bin-ordered vs caller-ordered, repeat angles" % name)

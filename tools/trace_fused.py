@@ -16,7 +16,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 TRACE_DIR = os.path.join(ROOT, "tools", "_trace")
-TRACE_LIB = os.path.join(TRACE_DIR, "librangelib_b200_trace.so")
+TRACE_LIB = os.environ.get("RL_TRACE_LIB") or os.path.join(TRACE_DIR, "librangelib_b200_trace.so")
 
 
 def build():
@@ -79,11 +79,19 @@ def run():
         a2 = np.concatenate([t[:, 10] for t, _ in rows])
         print("  steps at hand-off: median %.0f max %.0f | alive after first burst: median %.0f max %.0f | at hand-off: median %.0f max %.0f" % (
             np.median(steps), steps.max(), np.median(a1), a1.max(), np.median(a2), a2.max()))
+        nb, nf, ne = (np.concatenate([t[:, c] for t, _ in rows]) for c in (11, 12, 13))
+        print("  cooperative tail, per CTA: batches median %.0f max %.0f | replay steps median %.0f max %.0f | of them through "
+              "the exact test: %.1f %% overall (max CTA %.0f)" % (np.median(nb), nb.max(), np.median(nf), nf.max(),
+                                                                 100.0 * ne.sum() / max(nf.sum(), 1), ne.max()))
         # the slowest CTA of each launch
         for t, t0 in rows:
             k = int(np.argmax(t[:, 7]))
             print("  slowest CTA %4d: entry %5.0f march %5.0f burst1 %5.0f bursts %5.0f coop %5.0f stored %5.0f product %5.0f (steps %d, alive %d -> %d)" % (
                 k, t[k, 0] - t0, t[k, 1] - t0, t[k, 2] - t0, t[k, 3] - t0, t[k, 5] - t0, t[k, 6] - t0, t[k, 7] - t0, t[k, 8], t[k, 9], t[k, 10]))
+            print("                    tail of that CTA: %d batches, %d replay steps, %d through the exact test" % (t[k, 11], t[k, 12], t[k, 13]))
+            c14, c15 = int(t[k, 14]), int(t[k, 15])
+            print("                    its longest ray: %d steps in %d batches, %d cycles in the tail of which %d inside replay loops" % (
+                c15 >> 32, c15 & 0xffffffff, c14 >> 32, c14 & 0xffffffff))
 
 
 if __name__ == "__main__":
