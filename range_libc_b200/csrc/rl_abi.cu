@@ -355,6 +355,9 @@ static void free_method(rl_method* m) {
   cudaFree(m->d_epoch);
   cudaFree(m->d_counter);
   cudaFree(m->d_radial);
+  cudaFree(m->d_part);
+  cudaFree(m->d_part_bucket);
+  cudaFree(m->d_part_hist);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;

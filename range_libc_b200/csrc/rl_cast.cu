@@ -836,45 +836,110 @@ radial_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const flo
 // A query reads two offsets, the ends of its bin and ~log2(bin size) probes of a binary search.  With the queries
 // in caller order every one of those reads is its own DRAM sector (ncu, round 2: 534 B of DRAM traffic per query,
 // L2 hit rate 20 %, 8.4 G rays/s).  The bin a query lands in is cheap to compute (theta -> slice, one rotation), so
-// large batches are first ORDERED BY BIN: a key kernel writes (bin, ray index), a radix sort over the significant
-// key bits orders the pairs, and the cast kernel walks the sorted pairs -- the lanes of a warp then search the
-// same or neighbouring bins, their probes share lines (the upper levels of the search are the same address for
-// the whole warp), and the table streams through L2 once.  Each result is computed by cddt_cast as before and
-// stored at its ray's own index.
+// large batches are first PARTITIONED BY BIN RANGE -- north_star's "bucket the queries per theta bin":
+//   1. cddt_bucket_hist_kernel   ray -> (slice, bin) -> bucket = global bin index >> shift (<= 2048 buckets, each a
+//                                few hundred KB of table); per-CTA shared-memory histogram, one global add per bucket
+//   2. cddt_bucket_scan_kernel   exclusive scan of the bucket counts -> bucket cursors
+//   3. cddt_bucket_scatter_kernel  every CTA reserves a range per bucket (one global atomic per CTA and bucket) and
+//                                writes its rays' grid poses + ray index as 16-byte records into their bucket
+//   4. cddt_part_cast_kernel     walks the records: a warp's rays search the same few hundred bins, whose zero
+//                                points stay in L1 / L2 while the bucket is processed, and the table streams from HBM
+//                                once; each result is computed by cddt_cast as before and stored at its ray's index.
+// A first version sorted (bin, index) pairs with cub::DeviceRadixSort and gathered the poses in sorted order:
+// 12.3 G rays/s (key kernel 91 us + sort 335 us + cast 934 us for 2^24 rays: the gather of 12-byte poses cost more
+// DRAM traffic than the table itself).  The order of the records inside a bucket depends on the schedule; the
+// results do not -- every ray is computed by the same arithmetic and written to its own slot.
 // ------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(256)
-cddt_key_kernel(CddtView cv, WorldXform xf, const float* __restrict__ ins, const float* __restrict__ angles,
-                long long total, int M, unsigned sentinel, unsigned* __restrict__ keys, int* __restrict__ idx) {
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= total) return;
-  float x, y, th;
-  load_pose<MODE>(xf, ins, angles, r, M, &x, &y, &th);
-  unsigned key = sentinel;  // rays that never reach a bin (non-finite pose, rotated y outside the slice)
-  if (finite3(x, y, th)) {
-    int a;
-    bool flipped;
-    cddt_discretize(cv, -th, &a, &flipped);
-    const float ly = fadd(fadd(fmul(x, __ldg(cv.sinv + a)), fmul(y, __ldg(cv.cosv + a))), __ldg(cv.trans + a));
-    const unsigned li = (unsigned)f2i(ly);
-    if (li < (unsigned)__ldg(cv.widths + a)) key = (unsigned)(__ldg(cv.slice0 + a) + li);
-  }
-  keys[r] = key;
-  idx[r] = (int)r;
+#define RL_CDDT_MAX_BUCKETS 2048
+#define RL_CDDT_TILE 4096  // rays per CTA in the partition passes
+
+__device__ __forceinline__ unsigned cddt_bucket_of(const CddtView& cv, float x, float y, float th, int shift,
+                                                   unsigned no_bin_bucket) {
+  if (!finite3(x, y, th)) return no_bin_bucket;
+  int a;
+  bool flipped;
+  cddt_discretize(cv, -th, &a, &flipped);
+  const float ly = fadd(fadd(fmul(x, __ldg(cv.sinv + a)), fmul(y, __ldg(cv.cosv + a))), __ldg(cv.trans + a));
+  const unsigned li = (unsigned)f2i(ly);
+  if (li >= (unsigned)__ldg(cv.widths + a)) return no_bin_bucket;  // rotated y outside the slice: max_range, no table read
+  return (unsigned)((__ldg(cv.slice0 + a) + li) >> shift);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(256)
-cddt_sorted_cast_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float* __restrict__ ins,
-                        const float* __restrict__ angles, float* __restrict__ outs, const int* __restrict__ perm,
-                        long long total, int M) {
+cddt_bucket_hist_kernel(CddtView cv, WorldXform xf, const float* __restrict__ ins, const float* __restrict__ angles,
+                        long long total, int M, int shift, int nb, unsigned short* __restrict__ bucket_of,
+                        unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[RL_CDDT_MAX_BUCKETS + 1];
+  for (int b = threadIdx.x; b <= nb; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  const long long t0 = (long long)blockIdx.x * RL_CDDT_TILE;
+  for (int e = threadIdx.x; e < RL_CDDT_TILE && t0 + e < total; e += blockDim.x) {
+    float x, y, th;
+    load_pose<MODE>(xf, ins, angles, t0 + e, M, &x, &y, &th);
+    const unsigned b = cddt_bucket_of(cv, x, y, th, shift, (unsigned)nb);
+    bucket_of[t0 + e] = (unsigned short)b;
+    atomicAdd(&sh[b], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b <= nb; b += blockDim.x)
+    if (sh[b]) atomicAdd(&hist[b], sh[b]);
+}
+
+// one CTA: cursor[b] = sum of hist[0..b); hist is cleared for the next call
+__global__ void __launch_bounds__(1024)
+cddt_bucket_scan_kernel(unsigned* __restrict__ hist, unsigned* __restrict__ cursor, int n) {
+  __shared__ unsigned sh[RL_CDDT_MAX_BUCKETS + 2];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = hist[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned run = 0;
+    for (int i = 0; i < n; ++i) {
+      const unsigned c = sh[i];
+      sh[i] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    cursor[i] = sh[i];
+    hist[i] = 0;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+cddt_bucket_scatter_kernel(WorldXform xf, const float* __restrict__ ins, const float* __restrict__ angles,
+                           long long total, int M, int nb, const unsigned short* __restrict__ bucket_of,
+                           unsigned* __restrict__ cursor, float4* __restrict__ part) {
+  __shared__ unsigned cnt[RL_CDDT_MAX_BUCKETS + 1], base[RL_CDDT_MAX_BUCKETS + 1];
+  for (int b = threadIdx.x; b <= nb; b += blockDim.x) cnt[b] = 0;
+  __syncthreads();
+  const long long t0 = (long long)blockIdx.x * RL_CDDT_TILE;
+  for (int e = threadIdx.x; e < RL_CDDT_TILE && t0 + e < total; e += blockDim.x) atomicAdd(&cnt[bucket_of[t0 + e]], 1u);
+  __syncthreads();
+  for (int b = threadIdx.x; b <= nb; b += blockDim.x) {
+    const unsigned c = cnt[b];
+    base[b] = c ? atomicAdd(&cursor[b], c) : 0u;  // this CTA's range inside bucket b
+    cnt[b] = 0;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < RL_CDDT_TILE && t0 + e < total; e += blockDim.x) {
+    const unsigned b = bucket_of[t0 + e];
+    float x, y, th;
+    load_pose<MODE>(xf, ins, angles, t0 + e, M, &x, &y, &th);
+    const unsigned pos = base[b] + atomicAdd(&cnt[b], 1u);
+    part[pos] = make_float4(x, y, th, __int_as_float((int)(t0 + e)));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cddt_part_cast_kernel(MapView mv, CddtView cv, float max_range, float out_scale, const float4* __restrict__ part,
+                      float* __restrict__ outs, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const long long r = __ldg(perm + i);
-  float x, y, th;
-  load_pose<MODE>(xf, ins, angles, r, M, &x, &y, &th);
-  const float range = cddt_cast(mv, cv, max_range, x, y, th);
-  outs[r] = (MODE == MODE_GRID) ? range : fmul(range, xf.scale);
+  const float4 p = __ldg(part + i);
+  outs[__float_as_int(p.w)] = fmul(cddt_cast(mv, cv, max_range, p.x, p.y, p.z), out_scale);  // out_scale 1: exact
 }
 
 // One CTA handles `ppb` consecutive particles per iteration (grid-stride over particle groups).
@@ -1388,6 +1453,26 @@ static int block_burst_pairs() {  // tuning knob of rm_march_block (RL_BLOCK_BUR
   return v;
 }
 
+// scratch of the bin-range partition (CDDT on tables larger than L2): 16-byte records, bucket ids, histogram + cursors
+static int ensure_partition_buffers(rl_method* m, long long total) {
+  if (!m->d_part_hist) {
+    RL_CUDA(cudaMalloc(&m->d_part_hist, sizeof(unsigned) * 2 * (RL_CDDT_MAX_BUCKETS + 2)));
+    RL_CUDA(cudaMemsetAsync(m->d_part_hist, 0, sizeof(unsigned) * 2 * (RL_CDDT_MAX_BUCKETS + 2), m->stream));
+  }
+  if (total <= m->part_cap) return RL_OK;
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  cudaFree(m->d_part);
+  cudaFree(m->d_part_bucket);
+  m->d_part = nullptr;
+  m->d_part_bucket = nullptr;
+  m->part_cap = 0;
+  const long long cap = total + total / 8;
+  RL_CUDA(cudaMalloc(&m->d_part, sizeof(float4) * (size_t)cap));
+  RL_CUDA(cudaMalloc(&m->d_part_bucket, sizeof(unsigned short) * (size_t)cap));
+  m->part_cap = cap;
+  return RL_OK;
+}
+
 template <int KIND>
 static int launch_cast_kind(rl_method* m, int mode, const float* ins, const float* angles, const float* obs,
                             float* outs, double* weights, int n, int M, const PeerOut* peers) {
@@ -1445,37 +1530,34 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     }
   } else {
     const long long total = (mode == MODE_ANGLES) ? (long long)n * M : (long long)n;
-    // CDDT / PCDDT, big batch on a table larger than L2: bin-ordered processing (see cddt_key_kernel)
+    // CDDT / PCDDT, big batch on a table larger than L2: rays partitioned by bin range (see cddt_bucket_hist_kernel)
     static const bool cddt_sort = !(getenv("RL_CDDT_SORT") && atoi(getenv("RL_CDDT_SORT")) == 0);
     if (KIND == RL_CDDT && cddt_sort && m->spatial_sort && total >= (1LL << 18) && total < (1LL << 31) &&
-        (size_t)m->nvalues * sizeof(float) > ((size_t)48 << 20) && m->nbins < (int64_t)0xfffffff0u) {
-      unsigned* keys = nullptr;
-      int* idx = nullptr;
-      int rc = sort_buffers(m, (int)total, &keys, &idx);
+        (size_t)m->nvalues * sizeof(float) > ((size_t)48 << 20)) {
+      int rc = ensure_partition_buffers(m, total);
       if (rc) return rc;
-      const unsigned sentinel = (unsigned)m->nbins;
-      const unsigned kgrid = (unsigned)((total + 255) / 256);
-      if (mode == MODE_GRID)
-        cddt_key_kernel<MODE_GRID><<<kgrid, 256, 0, m->stream>>>(cv, m->xf, ins, angles, total, M, sentinel, keys, idx);
-      else if (mode == MODE_WORLD)
-        cddt_key_kernel<MODE_WORLD><<<kgrid, 256, 0, m->stream>>>(cv, m->xf, ins, angles, total, M, sentinel, keys, idx);
-      else
-        cddt_key_kernel<MODE_ANGLES><<<kgrid, 256, 0, m->stream>>>(cv, m->xf, ins, angles, total, M, sentinel, keys, idx);
-      count_launch();
+      int shift = 0;
+      while (((m->nbins + 1) >> shift) >= RL_CDDT_MAX_BUCKETS) ++shift;
+      const int nb = (int)((m->nbins >> shift) + 1);  // buckets 0 .. nb-1 hold bins, bucket nb the rays without a bin
+      const unsigned tiles = (unsigned)((total + RL_CDDT_TILE - 1) / RL_CDDT_TILE);
+      unsigned* hist = m->d_part_hist;
+      unsigned* cursor = hist + (RL_CDDT_MAX_BUCKETS + 2);
+#define RL_PARTITION(MD)                                                                                              \
+  do {                                                                                                                \
+    cddt_bucket_hist_kernel<MD><<<tiles, 256, 0, m->stream>>>(cv, m->xf, ins, angles, total, M, shift, nb,            \
+                                                              m->d_part_bucket, hist);                                \
+    cddt_bucket_scan_kernel<<<1, 1024, 0, m->stream>>>(hist, cursor, nb + 1);                                        \
+    cddt_bucket_scatter_kernel<MD><<<tiles, 256, 0, m->stream>>>(m->xf, ins, angles, total, M, nb, m->d_part_bucket, \
+                                                                 cursor, m->d_part);                                  \
+  } while (0)
+      if (mode == MODE_GRID) RL_PARTITION(MODE_GRID);
+      else if (mode == MODE_WORLD) RL_PARTITION(MODE_WORLD);
+      else RL_PARTITION(MODE_ANGLES);
+#undef RL_PARTITION
+      count_launch(3);
       RL_CHECK_LAUNCH();
-      int bits = 1;
-      while (bits < 32 && (1ull << bits) <= (unsigned long long)sentinel) ++bits;
-      // the top 16 key bits are enough: what matters is that a warp's bins are neighbours, not their exact order
-      static const int sort_bits = getenv("RL_CDDT_SORT_BITS") ? max(1, atoi(getenv("RL_CDDT_SORT_BITS"))) : 16;
-      const int* perm = nullptr;
-      rc = sort_pairs(m, (int)total, max(0, bits - sort_bits), bits, &perm);
-      if (rc) return rc;
-      if (mode == MODE_GRID)
-        cddt_sorted_cast_kernel<MODE_GRID><<<kgrid, 256, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, perm, total, M);
-      else if (mode == MODE_WORLD)
-        cddt_sorted_cast_kernel<MODE_WORLD><<<kgrid, 256, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, perm, total, M);
-      else
-        cddt_sorted_cast_kernel<MODE_ANGLES><<<kgrid, 256, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, perm, total, M);
+      cddt_part_cast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(
+          mv, cv, m->max_range, mode == MODE_GRID ? 1.0f : m->xf.scale, m->d_part, outs, total);
       count_launch();
       RL_CHECK_LAUNCH();
       return RL_OK;

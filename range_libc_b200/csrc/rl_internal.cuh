@@ -176,6 +176,11 @@ struct rl_method {
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   int sort_cap = 0;
+  // bin-range partition of big CDDT batches (rl_cast.cu)
+  float4* d_part = nullptr;
+  unsigned short* d_part_bucket = nullptr;
+  unsigned* d_part_hist = nullptr;
+  long long part_cap = 0;
   // calc_range_many_radial_optimized: beam-angle table of the last call
   float* d_radial = nullptr;
   int radial_cap = 0, radial_rays = -1, radial_count = 0;
@@ -218,8 +223,6 @@ int cddt_prune(rl_method* m, float max_range);
 void cddt_free(rl_method* m);
 // rl_sort.cu
 int spatial_order(rl_method* m, const float* d_ins, int n, const int** d_perm);
-int sort_buffers(rl_method* m, int n, unsigned** d_keys, int** d_idx);
-int sort_pairs(rl_method* m, int n, int begin_bit, int end_bit, const int** d_perm);
 void sort_free(rl_method* m);
 // rl_cast.cu -- the batched query kernels (all kinds, all modes)
 int launch_cast(rl_method* m, int mode, const float* d_ins, const float* d_angles, const float* d_obs, float* d_outs,

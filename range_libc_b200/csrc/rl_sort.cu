@@ -81,27 +81,6 @@ int spatial_order(rl_method* m, const float* d_ins, int n, const int** perm) {
   return RL_OK;
 }
 
-// Generic form used by the bin-ordered CDDT query (rl_cast.cu): the caller fills keys[0..n) / idx[0..n) obtained
-// from sort_buffers, then sort_pairs orders the pairs by key bits [begin_bit, end_bit).
-int sort_buffers(rl_method* m, int n, unsigned** keys, int** idx) {
-  int rc = ensure_sort_buffers(m, n);
-  if (rc) return rc;
-  *keys = m->d_sort_keys;
-  *idx = m->d_sort_idx;
-  return RL_OK;
-}
-
-int sort_pairs(rl_method* m, int n, int begin_bit, int end_bit, const int** perm) {
-  const int cap = m->sort_cap;
-  cub::DoubleBuffer<unsigned> k(m->d_sort_keys, m->d_sort_keys + cap);
-  cub::DoubleBuffer<int> v(m->d_sort_idx, m->d_sort_idx + cap);
-  size_t tb = m->sort_tmp_bytes;
-  RL_CUDA(cub::DeviceRadixSort::SortPairs(m->d_sort_tmp, tb, k, v, n, begin_bit, end_bit, m->stream));
-  count_launch(2);
-  *perm = v.Current();
-  return RL_OK;
-}
-
 void sort_free(rl_method* m) {
   cudaFree(m->d_sort_keys);
   cudaFree(m->d_sort_idx);

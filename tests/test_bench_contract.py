@@ -30,3 +30,16 @@ def test_other_ranks_of_the_reference_arm_stay_silent():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_reference_arm_config5_matches_the_gpu_arm_config():
+    """At N > 1 both arms run BASELINE config 5 (strong scaling); the `config` dict is the same object in both."""
+    sys.path.insert(0, ROOT)
+    import bench
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads(p.stdout.strip())
+    assert d["config"] == bench.workload_config("c5") and d["scaling"] == "strong" and d["n_gpus"] == 2
+    assert "50 000-particle" in d["cpu_baseline"]["sample"]
+    assert bench.workload_config("c2")["workload"].startswith("C2")

@@ -203,8 +203,8 @@ def test_multi_gpu_torchrun_all_gather_paths():
 
 @pytest.mark.parametrize("name,pruned", [("gigantic_map", False), ("huge_map", True)])
 def test_c3_bin_ordered_cddt_queries(name, pruned):
-    """C3: big CDDT / PCDDT batches on tables larger than L2 are processed in bin order (key kernel + radix sort +
-    sorted cast).  Only the processing order changes: the first 20 000 results reproduce the reference digests, the
+    """C3: big CDDT / PCDDT batches on tables larger than L2 are partitioned by bin range (histogram + scan + scatter +
+    cast of the partitioned records).  Only the processing order changes: the first 20 000 results reproduce the reference digests, the
     whole batch equals a launch in caller order, in grid, world and repeat-angles form."""
     import json
     import torch
