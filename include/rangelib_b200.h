@@ -80,6 +80,17 @@ int rl_method_create(int kind, const rl_map* map, float max_range, unsigned thet
 void rl_method_destroy(rl_method* m);
 /* CDDTCast::prune(max_range) RangeLib.h:1176 (PyCDDTCast.prune RangeLibc.pyx:263-267) */
 int rl_method_prune(rl_method* m, float max_range);
+/* Binary checkpoint of a built (and possibly pruned) CDDT table.  The reference can only dump the table as YAML /
+ * JSON text for its viewer (CDDTCast::serializeYaml / serializeJson RangeLib.h:1652-1735, main.cpp --cddt_save_path)
+ * and cannot load it back; this stores the same content (theta_discretization, lut_translations, max_range, map size,
+ * the sorted zero points of every bin) as the CSR arrays the kernels read.  rl_method_create_from_cddt builds a
+ * CDDT / PCDDT handle for `map` from such a file WITHOUT rebuilding or pruning; the file must have been written for
+ * the same occupancy grid (size and content hash are checked; RL_E_INVALID otherwise).  The map's world parameters
+ * are taken from `map` as in rl_method_create. */
+int rl_method_save_cddt(rl_method* m, const char* path);
+/* max_range / theta_discretization of a handle and whether its table has been pruned (any pointer may be NULL) */
+int rl_method_get_params(const rl_method* m, float* max_range, unsigned* theta_discretization, int* pruned);
+int rl_method_create_from_cddt(const rl_map* map, const char* path, int device, rl_method** out);
 /* run this handle's work on the given cudaStream_t (0 = CUDA's default stream).  A new handle
  * runs on a private non-blocking stream until this is called; rl_method_use_own_stream goes back. */
 int rl_method_set_stream(rl_method* m, void* cuda_stream);
@@ -201,7 +212,9 @@ int rl_debug_set_coop_threshold(rl_method* m, int rays);
  * one-ray-per-thread kernel (0).  Results are identical. */
 int rl_debug_set_persistent(rl_method* m, int on);
 /* tuning knob (fused call, clouds >= 32768 particles on structures larger than L2): process the particles in the
- * order of the 64x64-cell tile they stand in (default 1) or in caller order (0).  Results are identical. */
+ * order of the 64x64-cell tile they stand in (default 1) or in caller order (0).  CDDT / PCDDT: 0 searches the zero
+ * points directly even when the table is larger than L2 (default: through the L2-resident query index), 2 builds and
+ * uses the index whatever the table size (tests).  Results are identical. */
 int rl_debug_set_spatial_sort(rl_method* m, int on);
 /* GiantLUTCast::giant_lut (RangeLib.h:1903) as out[(x*H + y)*td + i], W*H*td uint16; HOST buffer */
 int rl_debug_glt_dump(rl_method* m, uint16_t* out);

@@ -302,8 +302,9 @@ class _RangeMethod:
         check(lib().rl_debug_set_persistent(self._h, int(on)))
 
     def set_spatial_sort(self, on):
-        """Tuning knob: tile-ordered processing of big clouds on > L2 structures (default on).  Results are identical."""
-        check(lib().rl_debug_set_spatial_sort(self._h, 1 if on else 0))
+        """Tuning knob: tile-ordered processing of big clouds on > L2 structures (default on); CDDT: False = no query
+        index, 2 = query index whatever the table size.  Results are identical."""
+        check(lib().rl_debug_set_spatial_sort(self._h, 2 if on == 2 else (1 if on else 0)))
 
     def set_coop_threshold(self, rays):
         """Tuning knob (RM, small launches): a CTA with <= rays live rays finishes them cooperatively (0 = off)."""
@@ -348,6 +349,24 @@ class PyCDDTCast(_RangeMethod):
 
     def prune(self, max_range=-1.0):
         check(lib().rl_method_prune(self._h, self.max_range if max_range < 0.0 else float(max_range)))
+
+    def save(self, path):
+        """Binary checkpoint of the (possibly pruned) table; see rl_method_save_cddt.  (The reference only dumps YAML /
+        JSON text for its viewer, RangeLib.h:1652-1735, and cannot load it back.)"""
+        check(lib().rl_method_save_cddt(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, Map, path, device=-1):
+        """A CDDT / PCDDT method for `Map` from a checkpoint written by save(): no rebuild, no prune."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self._L = lib()
+        self._map = Map
+        check(lib().rl_method_create_from_cddt(Map._h, str(path).encode(), int(device), C.byref(self._h)))
+        mr, td, pr = C.c_float(), C.c_uint(), C.c_int()
+        check(lib().rl_method_get_params(self._h, C.byref(mr), C.byref(td), C.byref(pr)))
+        self.max_range, self.theta_disc, self.pruned = mr.value, int(td.value), bool(pr.value)
+        return self
 
     def table(self):
         nb, nv = C.c_int64(), C.c_int64()

@@ -30,6 +30,9 @@ SIGNATURES = {
     "rl_method_create": (_i, [_i, _vp, _f, C.c_uint, _i, C.POINTER(_vp)]),
     "rl_method_destroy": (None, [_vp]),
     "rl_method_prune": (_i, [_vp, _f]),
+    "rl_method_save_cddt": (_i, [_vp, C.c_char_p]),
+    "rl_method_get_params": (_i, [_vp, C.POINTER(_f), C.POINTER(C.c_uint), C.POINTER(_i)]),
+    "rl_method_create_from_cddt": (_i, [_vp, C.c_char_p, _i, C.POINTER(_vp)]),
     "rl_method_set_stream": (_i, [_vp, _vp]),
     "rl_method_use_own_stream": (_i, [_vp]),
     "rl_method_synchronize": (_i, [_vp]),

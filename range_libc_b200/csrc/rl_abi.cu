@@ -355,9 +355,6 @@ static void free_method(rl_method* m) {
   cudaFree(m->d_epoch);
   cudaFree(m->d_counter);
   cudaFree(m->d_radial);
-  cudaFree(m->d_part);
-  cudaFree(m->d_part_bucket);
-  cudaFree(m->d_part_hist);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
@@ -497,6 +494,76 @@ int rl_method_create(int kind, const rl_map* map, float max_range, unsigned td, 
 
 void rl_method_destroy(rl_method* m) { free_method(m); }
 
+int rl_method_get_params(const rl_method* m, float* max_range, unsigned* theta_discretization, int* pruned) {
+  if (!m) return RL_E_INVALID;
+  if (max_range) *max_range = m->max_range;
+  if (theta_discretization) *theta_discretization = m->td;
+  if (pruned) *pruned = m->pruned ? 1 : 0;
+  return RL_OK;
+}
+
+int rl_method_save_cddt(rl_method* m, const char* path) {
+  DeviceGuard dg;
+  int rc = dg.bind(m);
+  if (rc) return rc;
+  if ((m->kind != RL_CDDT && m->kind != RL_PCDDT) || !path) {
+    set_error("rl_method_save_cddt: not a CDDT method / null path");
+    return RL_E_STATE;
+  }
+  return cddt_save(m, path);
+}
+
+int rl_method_create_from_cddt(const rl_map* map, const char* path, int device, rl_method** out) {
+  if (!map || !path || !out) {
+    set_error("rl_method_create_from_cddt: bad arguments");
+    return RL_E_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("rangelib_b200 needs a CUDA device (sm_100); there is no CPU fallback");
+    return RL_E_NO_DEVICE;
+  }
+  if (device < 0) RL_CUDA(cudaGetDevice(&device));
+  if (device >= ndev) {
+    set_error("rl_method_create_from_cddt: no such device");
+    return RL_E_INVALID;
+  }
+  int major = 0;
+  RL_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) {
+    set_error("rangelib_b200 is built for sm_100a only; this device is not a B200-class GPU");
+    return RL_E_NO_DEVICE;
+  }
+  DeviceGuard dg;
+  int rc = dg.bind(device);
+  if (rc) return rc;
+  rl_method* m = new rl_method();
+  m->kind = RL_CDDT;
+  m->device = device;
+  m->W = map->W;
+  m->H = map->H;
+  m->xf.inv_scale = (float)(1.0 / (double)map->scale);  // RangeLib.h:442-450, as in rl_method_create
+  m->xf.scale = map->scale;
+  m->xf.ox = map->ox;
+  m->xf.oy = map->oy;
+  m->xf.sin_a = map->sin_a;
+  m->xf.cos_a = map->cos_a;
+  m->xf.rot = (float)(-1.0 * (double)map->angle - 3.0 * RL_PI / 2.0);
+  e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) rc = cuda_fail(e, "stream create", __FILE__, __LINE__);
+  m->stream = m->own_stream;
+  if (!rc) rc = upload_occupancy(m, map);
+  if (!rc) rc = cddt_load(m, path);
+  if (rc) {
+    free_method(m);
+    return rc;
+  }
+  *out = m;
+  return RL_OK;
+}
+
 int rl_method_prune(rl_method* m, float max_range) {
   DeviceGuard dg;
   int rc = dg.bind(m);
@@ -585,6 +652,12 @@ int rl_debug_set_persistent(rl_method* m, int on) {
 int rl_debug_set_spatial_sort(rl_method* m, int on) {
   if (!m) return RL_E_INVALID;
   m->spatial_sort = on;
+  if (on == 2 && (m->kind == RL_CDDT || m->kind == RL_PCDDT) && !m->use_index) {  // tests: index on a small table
+    DeviceGuard dg;
+    int rc = dg.bind(m);
+    if (rc) return rc;
+    return cddt_index_build(m, true);
+  }
   return RL_OK;
 }
 
@@ -649,7 +722,7 @@ int64_t rl_method_memory(const rl_method* m) {
   int64_t bytes = (int64_t)m->W * m->H + (int64_t)m->tiles8_x() * m->tiles8_y() * 8;
   if (m->kind == RL_RM || m->kind == RL_GLT) bytes += (int64_t)m->dt_elems() * 4;
   if (m->kind == RL_GLT) bytes += (int64_t)m->W * m->H * m->td * 2;
-  if (m->kind == RL_CDDT || m->kind == RL_PCDDT) bytes += m->nvalues * 4 + (m->nbins + 1) * 8 + (int64_t)m->td * 16;
+  if (m->kind == RL_CDDT || m->kind == RL_PCDDT) bytes += m->nvalues * 4 + (m->nbins + 1) * 8 + (int64_t)m->td * 16 + ((m->use_index && m->spatial_sort) ? m->nbins * 16 + m->nskip * 4 : 0);
   return bytes;
 }
 

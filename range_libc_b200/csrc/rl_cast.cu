@@ -583,30 +583,114 @@ __device__ __forceinline__ void cddt_discretize(const CddtView& cv, float theta,
   *flipped = f;
 }
 
+// Search of one bin through the query index (rl_cddt.cu: cddt_index_build).  Returns the absolute position in
+// values[] of the first element of the bin [o0, o0 + size) that does NOT satisfy the bin-monotone predicate
+//   le ? v <= lx : v < lx        (o0 + size when all satisfy it)
+// which is o0 + the `lo` the plain bisections below end with.  skip[k] == values[16 k], so the blocks k0+1 .. k1 that
+// START inside the bin are bisected through skip[] (L2-resident), and the one 64-byte aligned block that holds the
+// boundary is read with 16-byte loads and counted branch-free; elements of the block that belong to the neighbouring
+// bins are masked out by position.
+#ifndef RL_CDDT_BLOCK_UNROLL
+#define RL_CDDT_BLOCK_UNROLL 4  // 16-byte loads of the block in flight at once (4: all; 1: one at a time, 12 registers less)
+#endif
+__device__ __forceinline__ unsigned cddt_search_indexed(const CddtView& cv, unsigned o0, unsigned size, float lx,
+                                                        bool le) {
+  const unsigned o1 = o0 + size;  // size >= 1
+  const unsigned k0 = o0 >> 4, k1 = (o1 - 1) >> 4;
+  const float* __restrict__ S = cv.skip + k0 + 1;
+  int lo = 0, n = (int)(k1 - k0);
+  while (n > 0) {
+    const int half = n >> 1;
+    const float v = __ldg(S + lo + half);
+    const bool go_right = le ? !(lx < v) : (v < lx);
+    lo = go_right ? lo + half + 1 : lo;
+    n = go_right ? n - half - 1 : half;
+  }
+  const unsigned kk = k0 + (unsigned)lo;  // the last block whose first element satisfies the predicate, or k0
+  const float4* __restrict__ blk = reinterpret_cast<const float4*>(cv.values + ((size_t)kk << 4));
+  const unsigned base = kk << 4;
+  const unsigned from = max(o0, base);
+  unsigned count = 0;
+  constexpr int kBlockUnroll = RL_CDDT_BLOCK_UNROLL;
+#pragma unroll kBlockUnroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 q = __ldg(blk + j);
+    const float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned idx = base + 4 * j + i;
+      const bool in = idx >= from && idx < o1;
+      const bool sat = le ? !(lx < e[i]) : (e[i] < lx);
+      count += (in && sat) ? 1u : 0u;
+    }
+  }
+  return from + count;
+}
+
+// the part of CDDTCast::calc_range that does not touch the table: theta -> slice, rotation, bin.  false: max_range.
+__device__ __forceinline__ bool cddt_locate(const CddtView& cv, float x, float y, float heading, bool* flipped,
+                                            float* lx, int64_t* bin) {
+  if (!finite3(x, y, heading)) return false;
+  int a;
+  cddt_discretize(cv, -heading, &a, flipped);
+  const float ca = __ldg(cv.cosv + a), sa = __ldg(cv.sinv + a);
+  *lx = fsub(fmul(x, ca), fmul(y, sa));
+  const float ly = fadd(fadd(fmul(x, sa), fmul(y, ca)), __ldg(cv.trans + a));
+  const unsigned li = (unsigned)f2i(ly);
+  if (li >= (unsigned)__ldg(cv.widths + a)) return false;
+  *bin = __ldg(cv.slice0 + a) + li;
+  return true;
+}
+
+// CDDTCast::calc_range through the query index (tables larger than L2): the same decisions as cddt_cast below, taken
+// from the bin's 16-byte record, the skip entries and one 64-byte block of zero points.  The occupancy word is
+// requested together with the record (its address only depends on the pose), not after the early exits.
+__device__ __forceinline__ float cddt_cast_indexed(const MapView& mv, const CddtView& cv, float max_range, float x,
+                                                   float y, float heading) {
+  bool flipped;
+  float lx;
+  int64_t b;
+  if (!cddt_locate(cv, x, y, heading, &flipped, &lx, &b)) return max_range;
+  const int cx = f2i(x), cy = f2i(y);
+  const bool inside = (unsigned)cx < (unsigned)mv.W && (unsigned)cy < (unsigned)mv.H;
+  const unsigned long long word = inside ? __ldg(mv.bits_t + (size_t)(cx >> 3) * mv.tiles8_y + (cy >> 3)) : 0ULL;
+  const uint4 mt = __ldg(reinterpret_cast<const uint4*>(cv.meta) + b);
+  const unsigned o0 = mt.x, size = mt.y;
+  if (size == 0) return max_range;
+  const float first = __uint_as_float(mt.z), last = __uint_as_float(mt.w);
+  bool le = true;
+  if (flipped) {
+    if (first > lx) return max_range;
+    if (last < lx) return fsub(lx, last);
+  } else {
+    if (last < lx) return max_range;
+    if (first > lx) return fsub(first, lx);
+    le = (int)size - 1 > RL_BINARY_SEARCH_THRESHOLD;
+  }
+  if ((word >> ((cx & 7) * 8 + (cy & 7))) & 1ULL) return 0.0f;  // map.grid[x][y] :1413 / :1475
+  const unsigned p = cddt_search_indexed(cv, o0, size, lx, le);
+  return flipped ? fsub(lx, __ldg(cv.values + p - 1)) : fsub(__ldg(cv.values + p), lx);
+}
+
 // CDDTCast::calc_range RangeLib.h:1342-1516.  cos/sin of the discrete angle come from the
 // host-tabulated libm values (cv.cosv/sinv), so trig is out of the parity question.
 __device__ __forceinline__ float cddt_cast(const MapView& mv, const CddtView& cv, float max_range, float x, float y,
                                            float heading) {
-  if (!finite3(x, y, heading)) return max_range;
-  int a;
+  if (cv.meta) return cddt_cast_indexed(mv, cv, max_range, x, y, heading);  // warp-uniform
   bool flipped;
-  cddt_discretize(cv, -heading, &a, &flipped);
-  const float ca = __ldg(cv.cosv + a), sa = __ldg(cv.sinv + a);
-  const float lx = fsub(fmul(x, ca), fmul(y, sa));
-  const float ly = fadd(fadd(fmul(x, sa), fmul(y, ca)), __ldg(cv.trans + a));
-  const unsigned li = (unsigned)f2i(ly);
-  if (li >= (unsigned)__ldg(cv.widths + a)) return max_range;
-  const int64_t b = __ldg(cv.slice0 + a) + li;
+  float lx;
+  int64_t b;
+  if (!cddt_locate(cv, x, y, heading, &flipped, &lx, &b)) return max_range;
+  // The reference scans bins of <= 65 entries linearly and uses std::upper_bound on larger ones.  A
+  // sorted, duplicate-free bin makes the linear scans equal to a binary search (first element >= lx,
+  // resp. last element <= lx), so every case below is one branch-free binary search; `strict` selects
+  // upper_bound (first element > lx) or lower_bound (first element >= lx).
   const int64_t o0 = __ldg(cv.offsets + b), o1 = __ldg(cv.offsets + b + 1);
   const float* __restrict__ B = cv.values + o0;
   const int size = (int)(o1 - o0);
   const int high = size - 1;
   if (high == -1) return max_range;
   const float first = __ldg(B), last = __ldg(B + high);
-  // The reference scans bins of <= 65 entries linearly and uses std::upper_bound on larger ones.  A
-  // sorted, duplicate-free bin makes the linear scans equal to a binary search (first element >= lx,
-  // resp. last element <= lx), so every case below is one branch-free binary search; `strict` selects
-  // upper_bound (first element > lx) or lower_bound (first element >= lx).
   if (flipped) {
     if (first > lx) return max_range;
     if (last < lx) return fsub(lx, last);
@@ -634,7 +718,7 @@ __device__ __forceinline__ float cddt_cast(const MapView& mv, const CddtView& cv
       lo = go_right ? lo + half + 1 : lo;
       n = go_right ? n - half - 1 : half;
     }
-    return fsub(__ldg(B + lo), lx);  // values[] is padded by one float: lo == size reads the pad
+    return fsub(__ldg(B + lo), lx);  // values[] is padded: lo == size reads the next bin's first value / the pad
   }
   return -1.0f;  // the reference's assert(0) fall-through (:1514)
 }
@@ -799,6 +883,28 @@ cast_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float
   }
 }
 
+// CDDT / PCDDT batches.  ncu on cast_kernel<CDDT> with the query index (profiles/r02/ncu_c3_cddt_index_first.txt):
+// nothing is saturated -- DRAM 36 %, L1->L2 requests 41 %, issue slots 28 % -- and 20 warps per scheduler-issue wait on
+// a load: a query is a chain of dependent misses (pose, bin record, skip entry, block of zero points; or pose, offsets,
+// bin ends, ~5 bisection probes without the index) and only 1024 of them fit an SM at cast_kernel's 56 registers.
+// This kernel carries nothing but the one CDDT path it is instantiated for and is bounded for 32 registers, so that
+// 2048 queries are in flight per SM.
+#ifndef RL_CDDT_IDX_MINB
+#define RL_CDDT_IDX_MINB 6  // resident CTAs per SM the register allocation is bounded for
+#endif
+template <int MODE, bool INDEXED>
+__global__ void __launch_bounds__(256, RL_CDDT_IDX_MINB)
+cddt_batch_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const float* __restrict__ ins,
+                    const float* __restrict__ angles, float* __restrict__ outs, long long total, int M) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += stride) {
+    float gx, gy, gth;
+    load_pose<MODE>(xf, ins, angles, r, M, &gx, &gy, &gth);
+    const float range = INDEXED ? cddt_cast_indexed(mv, cv, max_range, gx, gy, gth) : cddt_cast(mv, cv, max_range, gx, gy, gth);
+    outs[r] = (MODE == MODE_GRID) ? range : fmul(range, xf.scale);
+  }
+}
+
 // RangeMethod::calc_range_many_radial_optimized RangeLib.h:616-676.  Row i of outs (num_rays floats) gets, for
 // a <= max_pair, the pair (range at beam a, range at beam a + index_offset) from one calc_range_pair, and for
 // max_pair < a < index_offset a plain calc_range; beams the reference never writes are left untouched.
@@ -829,117 +935,6 @@ radial_kernel(MapView mv, CddtView cv, WorldXform xf, float max_range, const flo
       row[a] = fmul(cast_one<KIND>(mv, cv, max_range, y, x, th), xf.scale);
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------
-// CDDT / PCDDT on tables larger than L2 (BASELINE config 3: gigantic_map, 636 MB of zero points, 235 MB pruned).
-// A query reads two offsets, the ends of its bin and ~log2(bin size) probes of a binary search.  With the queries
-// in caller order every one of those reads is its own DRAM sector (ncu, round 2: 534 B of DRAM traffic per query,
-// L2 hit rate 20 %, 8.4 G rays/s).  The bin a query lands in is cheap to compute (theta -> slice, one rotation), so
-// large batches are first PARTITIONED BY BIN RANGE -- north_star's "bucket the queries per theta bin":
-//   1. cddt_bucket_hist_kernel   ray -> (slice, bin) -> bucket = global bin index >> shift (<= 2048 buckets, each a
-//                                few hundred KB of table); per-CTA shared-memory histogram, one global add per bucket
-//   2. cddt_bucket_scan_kernel   exclusive scan of the bucket counts -> bucket cursors
-//   3. cddt_bucket_scatter_kernel  every CTA reserves a range per bucket (one global atomic per CTA and bucket) and
-//                                writes its rays' grid poses + ray index as 16-byte records into their bucket
-//   4. cddt_part_cast_kernel     walks the records: a warp's rays search the same few hundred bins, whose zero
-//                                points stay in L1 / L2 while the bucket is processed, and the table streams from HBM
-//                                once; each result is computed by cddt_cast as before and stored at its ray's index.
-// A first version sorted (bin, index) pairs with cub::DeviceRadixSort and gathered the poses in sorted order:
-// 12.3 G rays/s (key kernel 91 us + sort 335 us + cast 934 us for 2^24 rays: the gather of 12-byte poses cost more
-// DRAM traffic than the table itself).  The order of the records inside a bucket depends on the schedule; the
-// results do not -- every ray is computed by the same arithmetic and written to its own slot.
-// ------------------------------------------------------------------------------------------
-#define RL_CDDT_MAX_BUCKETS 2048
-#define RL_CDDT_TILE 4096  // rays per CTA in the partition passes
-
-__device__ __forceinline__ unsigned cddt_bucket_of(const CddtView& cv, float x, float y, float th, int shift,
-                                                   unsigned no_bin_bucket) {
-  if (!finite3(x, y, th)) return no_bin_bucket;
-  int a;
-  bool flipped;
-  cddt_discretize(cv, -th, &a, &flipped);
-  const float ly = fadd(fadd(fmul(x, __ldg(cv.sinv + a)), fmul(y, __ldg(cv.cosv + a))), __ldg(cv.trans + a));
-  const unsigned li = (unsigned)f2i(ly);
-  if (li >= (unsigned)__ldg(cv.widths + a)) return no_bin_bucket;  // rotated y outside the slice: max_range, no table read
-  return (unsigned)((__ldg(cv.slice0 + a) + li) >> shift);
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(256)
-cddt_bucket_hist_kernel(CddtView cv, WorldXform xf, const float* __restrict__ ins, const float* __restrict__ angles,
-                        long long total, int M, int shift, int nb, unsigned short* __restrict__ bucket_of,
-                        unsigned* __restrict__ hist) {
-  __shared__ unsigned sh[RL_CDDT_MAX_BUCKETS + 1];
-  for (int b = threadIdx.x; b <= nb; b += blockDim.x) sh[b] = 0;
-  __syncthreads();
-  const long long t0 = (long long)blockIdx.x * RL_CDDT_TILE;
-  for (int e = threadIdx.x; e < RL_CDDT_TILE && t0 + e < total; e += blockDim.x) {
-    float x, y, th;
-    load_pose<MODE>(xf, ins, angles, t0 + e, M, &x, &y, &th);
-    const unsigned b = cddt_bucket_of(cv, x, y, th, shift, (unsigned)nb);
-    bucket_of[t0 + e] = (unsigned short)b;
-    atomicAdd(&sh[b], 1u);
-  }
-  __syncthreads();
-  for (int b = threadIdx.x; b <= nb; b += blockDim.x)
-    if (sh[b]) atomicAdd(&hist[b], sh[b]);
-}
-
-// one CTA: cursor[b] = sum of hist[0..b); hist is cleared for the next call
-__global__ void __launch_bounds__(1024)
-cddt_bucket_scan_kernel(unsigned* __restrict__ hist, unsigned* __restrict__ cursor, int n) {
-  __shared__ unsigned sh[RL_CDDT_MAX_BUCKETS + 2];
-  for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = hist[i];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned run = 0;
-    for (int i = 0; i < n; ++i) {
-      const unsigned c = sh[i];
-      sh[i] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    cursor[i] = sh[i];
-    hist[i] = 0;
-  }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(256)
-cddt_bucket_scatter_kernel(WorldXform xf, const float* __restrict__ ins, const float* __restrict__ angles,
-                           long long total, int M, int nb, const unsigned short* __restrict__ bucket_of,
-                           unsigned* __restrict__ cursor, float4* __restrict__ part) {
-  __shared__ unsigned cnt[RL_CDDT_MAX_BUCKETS + 1], base[RL_CDDT_MAX_BUCKETS + 1];
-  for (int b = threadIdx.x; b <= nb; b += blockDim.x) cnt[b] = 0;
-  __syncthreads();
-  const long long t0 = (long long)blockIdx.x * RL_CDDT_TILE;
-  for (int e = threadIdx.x; e < RL_CDDT_TILE && t0 + e < total; e += blockDim.x) atomicAdd(&cnt[bucket_of[t0 + e]], 1u);
-  __syncthreads();
-  for (int b = threadIdx.x; b <= nb; b += blockDim.x) {
-    const unsigned c = cnt[b];
-    base[b] = c ? atomicAdd(&cursor[b], c) : 0u;  // this CTA's range inside bucket b
-    cnt[b] = 0;
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < RL_CDDT_TILE && t0 + e < total; e += blockDim.x) {
-    const unsigned b = bucket_of[t0 + e];
-    float x, y, th;
-    load_pose<MODE>(xf, ins, angles, t0 + e, M, &x, &y, &th);
-    const unsigned pos = base[b] + atomicAdd(&cnt[b], 1u);
-    part[pos] = make_float4(x, y, th, __int_as_float((int)(t0 + e)));
-  }
-}
-
-__global__ void __launch_bounds__(256)
-cddt_part_cast_kernel(MapView mv, CddtView cv, float max_range, float out_scale, const float4* __restrict__ part,
-                      float* __restrict__ outs, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const float4 p = __ldg(part + i);
-  outs[__float_as_int(p.w)] = fmul(cddt_cast(mv, cv, max_range, p.x, p.y, p.z), out_scale);  // out_scale 1: exact
 }
 
 // One CTA handles `ppb` consecutive particles per iteration (grid-stride over particle groups).
@@ -1453,26 +1448,6 @@ static int block_burst_pairs() {  // tuning knob of rm_march_block (RL_BLOCK_BUR
   return v;
 }
 
-// scratch of the bin-range partition (CDDT on tables larger than L2): 16-byte records, bucket ids, histogram + cursors
-static int ensure_partition_buffers(rl_method* m, long long total) {
-  if (!m->d_part_hist) {
-    RL_CUDA(cudaMalloc(&m->d_part_hist, sizeof(unsigned) * 2 * (RL_CDDT_MAX_BUCKETS + 2)));
-    RL_CUDA(cudaMemsetAsync(m->d_part_hist, 0, sizeof(unsigned) * 2 * (RL_CDDT_MAX_BUCKETS + 2), m->stream));
-  }
-  if (total <= m->part_cap) return RL_OK;
-  RL_CUDA(cudaStreamSynchronize(m->stream));
-  cudaFree(m->d_part);
-  cudaFree(m->d_part_bucket);
-  m->d_part = nullptr;
-  m->d_part_bucket = nullptr;
-  m->part_cap = 0;
-  const long long cap = total + total / 8;
-  RL_CUDA(cudaMalloc(&m->d_part, sizeof(float4) * (size_t)cap));
-  RL_CUDA(cudaMalloc(&m->d_part_bucket, sizeof(unsigned short) * (size_t)cap));
-  m->part_cap = cap;
-  return RL_OK;
-}
-
 template <int KIND>
 static int launch_cast_kind(rl_method* m, int mode, const float* ins, const float* angles, const float* obs,
                             float* outs, double* weights, int n, int M, const PeerOut* peers) {
@@ -1530,38 +1505,6 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     }
   } else {
     const long long total = (mode == MODE_ANGLES) ? (long long)n * M : (long long)n;
-    // CDDT / PCDDT, big batch on a table larger than L2: rays partitioned by bin range (see cddt_bucket_hist_kernel)
-    static const bool cddt_sort = !(getenv("RL_CDDT_SORT") && atoi(getenv("RL_CDDT_SORT")) == 0);
-    if (KIND == RL_CDDT && cddt_sort && m->spatial_sort && total >= (1LL << 18) && total < (1LL << 31) &&
-        (size_t)m->nvalues * sizeof(float) > ((size_t)48 << 20)) {
-      int rc = ensure_partition_buffers(m, total);
-      if (rc) return rc;
-      int shift = 0;
-      while (((m->nbins + 1) >> shift) >= RL_CDDT_MAX_BUCKETS) ++shift;
-      const int nb = (int)((m->nbins >> shift) + 1);  // buckets 0 .. nb-1 hold bins, bucket nb the rays without a bin
-      const unsigned tiles = (unsigned)((total + RL_CDDT_TILE - 1) / RL_CDDT_TILE);
-      unsigned* hist = m->d_part_hist;
-      unsigned* cursor = hist + (RL_CDDT_MAX_BUCKETS + 2);
-#define RL_PARTITION(MD)                                                                                              \
-  do {                                                                                                                \
-    cddt_bucket_hist_kernel<MD><<<tiles, 256, 0, m->stream>>>(cv, m->xf, ins, angles, total, M, shift, nb,            \
-                                                              m->d_part_bucket, hist);                                \
-    cddt_bucket_scan_kernel<<<1, 1024, 0, m->stream>>>(hist, cursor, nb + 1);                                        \
-    cddt_bucket_scatter_kernel<MD><<<tiles, 256, 0, m->stream>>>(m->xf, ins, angles, total, M, nb, m->d_part_bucket, \
-                                                                 cursor, m->d_part);                                  \
-  } while (0)
-      if (mode == MODE_GRID) RL_PARTITION(MODE_GRID);
-      else if (mode == MODE_WORLD) RL_PARTITION(MODE_WORLD);
-      else RL_PARTITION(MODE_ANGLES);
-#undef RL_PARTITION
-      count_launch(3);
-      RL_CHECK_LAUNCH();
-      cddt_part_cast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(
-          mv, cv, m->max_range, mode == MODE_GRID ? 1.0f : m->xf.scale, m->d_part, outs, total);
-      count_launch();
-      RL_CHECK_LAUNCH();
-      return RL_OK;
-    }
     // RM with enough rays to give every resident warp more than one ray per lane: persistent
     // warps with lane re-queuing.  (max_range <= 0 never enters the marching loop.)
     if (KIND == RL_BL && total >= (long long)sm_count() * 40 * 64 && m->persist) {
@@ -1613,6 +1556,22 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     }
     const long long blocks = (total + threads - 1) / threads;
     const int grid = (int)max(1LL, min(blocks, (long long)sm_count() * 8 * 64));
+    if (KIND == RL_CDDT && (cv.meta || total >= 65536)) {  // big batches, and every batch on a table larger than L2
+#define RL_LAUNCH_CDDT(MD)                                                                                              \
+  do {                                                                                                                  \
+    if (cv.meta)                                                                                                        \
+      cddt_batch_kernel<MD, true><<<grid, threads, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, total, M);  \
+    else                                                                                                                \
+      cddt_batch_kernel<MD, false><<<grid, threads, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, total, M); \
+  } while (0)
+      if (mode == MODE_GRID) RL_LAUNCH_CDDT(MODE_GRID);
+      else if (mode == MODE_WORLD) RL_LAUNCH_CDDT(MODE_WORLD);
+      else RL_LAUNCH_CDDT(MODE_ANGLES);
+#undef RL_LAUNCH_CDDT
+      count_launch();
+      RL_CHECK_LAUNCH();
+      return RL_OK;
+    }
     if (mode == MODE_GRID)
       cast_kernel<KIND, MODE_GRID><<<grid, threads, 0, m->stream>>>(mv, cv, m->xf, m->max_range, ins, angles, outs, total, M);
     else if (mode == MODE_WORLD)

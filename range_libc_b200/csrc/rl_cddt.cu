@@ -14,10 +14,17 @@
 
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
 #include "rl_internal.cuh"
 #include "rl_math.cuh"
 
 namespace rl {
+
+void cddt_free(rl_method* m);
+
 
 namespace {
 
@@ -287,6 +294,207 @@ inline int slices_to_fill(unsigned td) {  // the reference iterates a < td / 2.0
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------
+// Query index (round 2).  On BASELINE config 3 the zero points (636 MB, 235 MB pruned) do not fit L2, and a query used
+// to touch ~9 separate DRAM sectors: two offsets, the bin's first and last value, and the probes of a binary search
+// over ~200 values (ncu: 534 B of DRAM traffic per query, 8.4 G rays/s, DRAM 54 % busy on 32-byte gathers).
+// Partitioning the queries by bin first (key + radix sort, then a hand-written histogram / scatter) made the table
+// stream through L2 once, but the partition itself cost as much as it saved (12.3 and 13.6 G rays/s).  The index
+// makes the part of the search that decides WHERE to look small enough to live in L2:
+//   meta[bin]  one 16-byte record: offset, size, first and last value of the bin            (13 MB on C3)
+//   skip[k]    values[16 k]: the first value of every 64-byte aligned block of values[]     (40 MB on C3, 15 MB pruned)
+// A query reads its record (the early exits need nothing else), bisects the skip entries of the blocks that start
+// inside its bin (L2), and then reads the ONE aligned 64-byte block of values[] that holds its answer with four
+// 16-byte loads -- one DRAM access instead of nine.  The search returns the same element as before: its predicate is
+// monotone along a bin, so "count the blocks whose first element satisfies it, then the elements inside the last such
+// block" is the same bisection split in two (cddt_search_indexed, rl_cast.cu).
+// ------------------------------------------------------------------------------------------
+namespace {
+__global__ void index_meta_kernel(const int64_t* __restrict__ off, const float* __restrict__ vals, int64_t nbins,
+                                  CddtBinMeta* __restrict__ meta) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbins) return;
+  const int64_t o0 = off[b];
+  const unsigned size = (unsigned)(off[b + 1] - o0);
+  CddtBinMeta mt;
+  mt.off = (unsigned)o0;
+  mt.size = size;
+  mt.first = size ? vals[o0] : 0.0f;
+  mt.last = size ? vals[o0 + size - 1] : 0.0f;
+  meta[b] = mt;
+}
+__global__ void index_skip_kernel(const float* __restrict__ vals, int64_t nskip, float* __restrict__ skip) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nskip) skip[k] = vals[k * RL_CDDT_BLOCK];
+}
+}  // namespace
+
+int cddt_index_build(rl_method* m, bool force_on) {
+  cudaFree(m->d_meta);
+  cudaFree(m->d_skip);
+  m->d_meta = nullptr;
+  m->d_skip = nullptr;
+  m->nskip = 0;
+  m->use_index = false;
+  const int64_t nbins = m->nbins;
+  if (nbins == 0 || m->nvalues >= 0xfffffff0LL) return RL_OK;  // no index: plain search
+  // tables that fit L2 are searched directly (one pass less through L2 per query); RL_CDDT_INDEX=1 / 0 forces
+  static const int force = getenv("RL_CDDT_INDEX") ? atoi(getenv("RL_CDDT_INDEX")) : -1;
+  const bool want = force_on ? true : force >= 0 ? force != 0 : (size_t)m->nvalues * sizeof(float) > ((size_t)48 << 20);
+  if (!want) return RL_OK;
+  cudaStream_t st = m->stream;
+  const int64_t nskip = (int64_t)(cddt_values_alloc(m->nvalues) / RL_CDDT_BLOCK);
+  RL_CUDA(cudaMalloc(&m->d_meta, sizeof(CddtBinMeta) * (size_t)nbins));
+  RL_CUDA(cudaMalloc(&m->d_skip, sizeof(float) * (size_t)nskip));
+  index_meta_kernel<<<blocks_for(nbins, 256), 256, 0, st>>>(m->d_offsets, m->d_values, nbins, m->d_meta);
+  index_skip_kernel<<<blocks_for(nskip, 256), 256, 0, st>>>(m->d_values, nskip, m->d_skip);
+  count_launch(2);
+  RL_CHECK_LAUNCH();
+  RL_CUDA(cudaStreamSynchronize(st));
+  m->nskip = nskip;
+  m->use_index = true;
+  return RL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Binary checkpoint of a built (and possibly pruned) table.  The reference can only dump its table as YAML / JSON text
+// for a viewer (CDDTCast::serializeYaml / serializeJson, RangeLib.h:1652-1735, helpers RangeUtils.h:210-238) and has no
+// loader; the content is the same -- theta_discretization, lut_translations, max_range, map size, and per slice and bin
+// the sorted zero points -- stored as the CSR arrays the kernels read, so that a PCDDT table whose prune takes the CPU
+// reference 24 minutes on gigantic_map is loaded without rebuilding.
+//   header  : magic "RLCDDT\0\1", u32 version, u32 theta_discretization, i32 W, i32 H, f32 max_range, u32 pruned,
+//             u64 FNV-1a of the occupancy bytes, i64 nbins, i64 nvalues
+//   payload : i32 widths[td], f32 translations[td], i64 offsets[nbins + 1], f32 values[nvalues]   (little endian)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct CkptHeader {
+  char magic[8];
+  uint32_t version, td;
+  int32_t W, H;
+  float max_range;
+  uint32_t pruned;
+  uint64_t occ_hash;
+  int64_t nbins, nvalues;
+};
+const char kMagic[8] = {'R', 'L', 'C', 'D', 'D', 'T', 0, 1};
+
+uint64_t fnv1a(const uint8_t* p, size_t n) {
+  uint64_t h = 1469598103934665603ULL;
+  for (size_t i = 0; i < n; ++i) h = (h ^ (uint64_t)(p[i] ? 1 : 0)) * 1099511628211ULL;
+  return h;
+}
+}  // namespace
+
+int cddt_save(rl_method* m, const char* path) {
+  const size_t cells = (size_t)m->W * m->H;
+  std::vector<uint8_t> occ(cells ? cells : 1);
+  std::vector<int64_t> off((size_t)m->nbins + 1);
+  std::vector<float> vals((size_t)m->nvalues ? (size_t)m->nvalues : 1);
+  if (cells) RL_CUDA(cudaMemcpyAsync(occ.data(), m->d_occ, cells, cudaMemcpyDeviceToHost, m->stream));
+  RL_CUDA(cudaMemcpyAsync(off.data(), m->d_offsets, sizeof(int64_t) * off.size(), cudaMemcpyDeviceToHost, m->stream));
+  if (m->nvalues)
+    RL_CUDA(cudaMemcpyAsync(vals.data(), m->d_values, sizeof(float) * (size_t)m->nvalues, cudaMemcpyDeviceToHost, m->stream));
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  CkptHeader h{};
+  memcpy(h.magic, kMagic, 8);
+  h.version = 1;
+  h.td = m->td;
+  h.W = m->W;
+  h.H = m->H;
+  h.max_range = m->max_range;
+  h.pruned = m->pruned ? 1u : 0u;
+  h.occ_hash = fnv1a(occ.data(), cells);
+  h.nbins = m->nbins;
+  h.nvalues = m->nvalues;
+  FILE* f = fopen(path, "wb");
+  if (!f) {
+    set_error(std::string("cannot open for writing: ") + path);
+    return RL_E_INVALID;
+  }
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+  ok = ok && fwrite(m->h_widths.data(), sizeof(int), m->td, f) == m->td;
+  ok = ok && fwrite(m->h_trans.data(), sizeof(float), m->td, f) == m->td;
+  ok = ok && fwrite(off.data(), sizeof(int64_t), off.size(), f) == off.size();
+  ok = ok && (m->nvalues == 0 || fwrite(vals.data(), sizeof(float), (size_t)m->nvalues, f) == (size_t)m->nvalues);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) {
+    set_error(std::string("short write: ") + path);
+    return RL_E_INVALID;
+  }
+  return RL_OK;
+}
+
+// fills the CDDT part of a handle whose occupancy is already resident from a checkpoint written by cddt_save
+int cddt_load(rl_method* m, const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) {
+    set_error(std::string("cannot open: ") + path);
+    return RL_E_INVALID;
+  }
+  struct Closer {
+    FILE* f;
+    ~Closer() { fclose(f); }
+  } closer{f};
+  CkptHeader h{};
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kMagic, 8) != 0 || h.version != 1) {
+    set_error("not a CDDT checkpoint (magic / version)");
+    return RL_E_INVALID;
+  }
+  if (h.W != m->W || h.H != m->H || h.td == 0 || h.nbins < 0 || h.nvalues < 0) {
+    set_error("CDDT checkpoint: map size differs from the map passed in");
+    return RL_E_INVALID;
+  }
+  const size_t cells = (size_t)m->W * m->H;
+  std::vector<uint8_t> occ(cells ? cells : 1);
+  if (cells) RL_CUDA(cudaMemcpyAsync(occ.data(), m->d_occ, cells, cudaMemcpyDeviceToHost, m->stream));
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  if (fnv1a(occ.data(), cells) != h.occ_hash) {
+    set_error("CDDT checkpoint: it was built from a different occupancy grid");
+    return RL_E_INVALID;
+  }
+  cddt_free(m);
+  m->td = h.td;
+  m->max_range = h.max_range;
+  int rc = upload_consts(m);  // per-slice constants are recomputed (host libm, as at build time) and cross-checked
+  if (rc) return rc;
+  std::vector<int> widths(h.td);
+  std::vector<float> trans(h.td);
+  if (fread(widths.data(), sizeof(int), h.td, f) != h.td || fread(trans.data(), sizeof(float), h.td, f) != h.td) {
+    set_error("CDDT checkpoint: truncated");
+    return RL_E_INVALID;
+  }
+  if (m->nbins != h.nbins || memcmp(widths.data(), m->h_widths.data(), sizeof(int) * h.td) != 0 ||
+      memcmp(trans.data(), m->h_trans.data(), sizeof(float) * h.td) != 0) {
+    set_error("CDDT checkpoint: slice geometry differs from what this build derives for the map");
+    return RL_E_INVALID;
+  }
+  std::vector<int64_t> off((size_t)h.nbins + 1);
+  std::vector<float> vals(cddt_values_alloc(h.nvalues), 0.0f);  // + the pad element / last aligned block cddt_cast may read
+  if (fread(off.data(), sizeof(int64_t), off.size(), f) != off.size() ||
+      (h.nvalues && fread(vals.data(), sizeof(float), (size_t)h.nvalues, f) != (size_t)h.nvalues)) {
+    set_error("CDDT checkpoint: truncated");
+    return RL_E_INVALID;
+  }
+  if (off[0] != 0 || off[(size_t)h.nbins] != h.nvalues) {
+    set_error("CDDT checkpoint: inconsistent offsets");
+    return RL_E_INVALID;
+  }
+  for (size_t i = 0; i < (size_t)h.nbins; ++i) {
+    if (off[i] > off[i + 1]) {
+      set_error("CDDT checkpoint: inconsistent offsets");
+      return RL_E_INVALID;
+    }
+  }
+  RL_CUDA(cudaMalloc(&m->d_offsets, sizeof(int64_t) * off.size()));
+  RL_CUDA(cudaMalloc(&m->d_values, sizeof(float) * vals.size()));
+  RL_CUDA(cudaMemcpyAsync(m->d_offsets, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, m->stream));
+  RL_CUDA(cudaMemcpyAsync(m->d_values, vals.data(), sizeof(float) * vals.size(), cudaMemcpyHostToDevice, m->stream));
+  RL_CUDA(cudaStreamSynchronize(m->stream));
+  m->nvalues = h.nvalues;
+  m->pruned = h.pruned != 0;
+  return cddt_index_build(m);
+}
+
 void cddt_free(rl_method* m) {
   cudaFree(m->d_widths);
   cudaFree(m->d_trans);
@@ -295,6 +503,11 @@ void cddt_free(rl_method* m) {
   cudaFree(m->d_slice0);
   cudaFree(m->d_offsets);
   cudaFree(m->d_values);
+  cudaFree(m->d_meta);
+  cudaFree(m->d_skip);
+  m->d_meta = nullptr;
+  m->d_skip = nullptr;
+  m->nskip = 0;
   m->d_widths = nullptr;
   m->d_trans = m->d_cosv = m->d_sinv = nullptr;
   m->d_slice0 = m->d_offsets = nullptr;
@@ -413,8 +626,8 @@ int cddt_build(rl_method* m) {
   RL_CUDA(cudaMemcpyAsync(&nvalues, m->d_offsets + nbins, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   RL_CUDA(cudaStreamSynchronize(st));
   m->nvalues = nvalues;
-  RL_CUDA(cudaMalloc(&m->d_values, sizeof(float) * ((size_t)nvalues + 1)));  // +1 pad, see cddt_cast
-  RL_CUDA(cudaMemsetAsync(m->d_values + nvalues, 0, sizeof(float), st));
+  RL_CUDA(cudaMalloc(&m->d_values, sizeof(float) * cddt_values_alloc(nvalues)));  // pad, see cddt_cast
+  RL_CUDA(cudaMemsetAsync(m->d_values + nvalues, 0, sizeof(float) * (cddt_values_alloc(nvalues) - (size_t)nvalues), st));
   if (nbins > 0 && nvalues > 0) {
     compact_kernel<false><<<blocks_for(nbins * 32, 256), 256, 0, st>>>(d_sorted, d_raw_off, nbins, nullptr, m->d_offsets,
                                                                       m->d_values);
@@ -422,7 +635,7 @@ int cddt_build(rl_method* m) {
     RL_CHECK_LAUNCH();
   }
   RL_CUDA(cudaStreamSynchronize(st));
-  return RL_OK;
+  return cddt_index_build(m);
 }
 
 int cddt_prune(rl_method* m, float max_range) {
@@ -487,12 +700,12 @@ int cddt_prune(rl_method* m, float max_range) {
   cudaError_t e = cudaMemcpyAsync(&nvalues, d_new_off + nbins, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   float* d_new_vals = nullptr;
-  if (e == cudaSuccess) e = cudaMalloc(&d_new_vals, sizeof(float) * ((size_t)nvalues + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_new_vals, sizeof(float) * cddt_values_alloc(nvalues));
   if (e != cudaSuccess) {
     cudaFree(d_new_off);
     return cuda_fail(e, "prune alloc", __FILE__, __LINE__);
   }
-  cudaMemsetAsync(d_new_vals + nvalues, 0, sizeof(float), st);
+  cudaMemsetAsync(d_new_vals + nvalues, 0, sizeof(float) * (cddt_values_alloc(nvalues) - (size_t)nvalues), st);
   compact_kernel<true><<<blocks_for(nbins * 32, 256), 256, 0, st>>>(m->d_values, m->d_offsets, nbins, d_used, d_new_off,
                                                                    d_new_vals);
   count_launch();
@@ -509,7 +722,7 @@ int cddt_prune(rl_method* m, float max_range) {
   m->d_values = d_new_vals;
   m->nvalues = nvalues;
   m->pruned = true;
-  return RL_OK;
+  return cddt_index_build(m);
 }
 
 }  // namespace rl

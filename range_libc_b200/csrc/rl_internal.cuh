@@ -68,6 +68,19 @@ struct MapView {
   int block_burst_pairs = 6;  // rm_march_block: own-ray steps between two CTA-wide counts = 2 * this
 };
 
+// Per-bin record of the L2-resident query index (rl_cddt.cu: cddt_index_build): everything a query needs to know
+// about its bin before it touches the zero points themselves, in one 16-byte load.
+struct __align__(16) CddtBinMeta {
+  unsigned off;   // first zero point of the bin in values[]
+  unsigned size;  // number of zero points
+  float first, last;
+};
+#define RL_CDDT_BLOCK 16  // zero points per skip entry: one aligned 64-byte block of values[]
+// values[] is allocated with this many floats so that the last aligned block and the pad element exist
+inline size_t cddt_values_alloc(int64_t nvalues) {
+  return (((size_t)nvalues + RL_CDDT_BLOCK) / RL_CDDT_BLOCK + 1) * RL_CDDT_BLOCK;
+}
+
 struct CddtView {
   unsigned td;
   const int* widths;        // [td]
@@ -79,6 +92,8 @@ struct CddtView {
   const float* values;      // [nvalues + pad]
   float td_div_2pi;         // (float)(td / M_2PI)           RangeLib.h:976
   float twopi_div_td;       // (float)(M_2PI / (float)td)    RangeLib.h:977
+  const CddtBinMeta* meta;  // [nbins] query index, or nullptr: search values[] directly
+  const float* skip;        // skip[k] = values[16 k]
 };
 
 struct SensorView {
@@ -150,6 +165,10 @@ struct rl_method {
   int64_t *d_slice0 = nullptr, *d_offsets = nullptr;
   float* d_values = nullptr;
   int64_t nbins = 0, nvalues = 0;
+  rl::CddtBinMeta* d_meta = nullptr;  // query index over the table (rebuilt whenever the table changes)
+  float* d_skip = nullptr;
+  int64_t nskip = 0;
+  bool use_index = false;  // queries go through the index (tables larger than L2; RL_CDDT_INDEX=0|1 overrides)
   std::vector<int> h_widths;
   std::vector<float> h_trans, h_cosv, h_sinv;
   std::vector<int64_t> h_slice0;
@@ -176,11 +195,6 @@ struct rl_method {
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   int sort_cap = 0;
-  // bin-range partition of big CDDT batches (rl_cast.cu)
-  float4* d_part = nullptr;
-  unsigned short* d_part_bucket = nullptr;
-  unsigned* d_part_hist = nullptr;
-  long long part_cap = 0;
   // calc_range_many_radial_optimized: beam-angle table of the last call
   float* d_radial = nullptr;
   int radial_cap = 0, radial_rays = -1, radial_count = 0;
@@ -190,7 +204,7 @@ struct rl_method {
 
   size_t dt_elems() const { return (size_t)W * H; }
   int coop_threshold = 8;
-  int spatial_sort = 1;  // big clouds on > L2 structures are processed in tile order (rl_sort.cu)
+  int spatial_sort = 1;  // big clouds on > L2 structures are processed in tile order (rl_sort.cu); 0 also switches the CDDT query index off
   int persist = 1;  // RM large batches: 0 one ray per thread, 1 persistent warps with lane re-queuing
   rl::MapView map_view() const {
     rl::MapView v{W, H, d_occ, d_bits_t, tiles8_y(), d_dt, coop_threshold, d_glt, td, 0.f, 0.f, 0.f, 0.f};
@@ -203,7 +217,8 @@ struct rl_method {
     return v;
   }
   rl::CddtView cddt_view() const {
-    return rl::CddtView{td, d_widths, d_trans, d_cosv, d_sinv, d_slice0, d_offsets, d_values, td_div_2pi, twopi_div_td};
+    return rl::CddtView{td, d_widths, d_trans, d_cosv, d_sinv, d_slice0, d_offsets, d_values, td_div_2pi, twopi_div_td,
+                        (use_index && spatial_sort) ? d_meta : nullptr, d_skip};
   }
   rl::SensorView sensor_view() const { return rl::SensorView{d_table, K}; }
 };
@@ -221,6 +236,9 @@ int apply_patch_batch(rl_method* m, const uint8_t* d_patches, const int* d_rects
 int cddt_build(rl_method* m);
 int cddt_prune(rl_method* m, float max_range);
 void cddt_free(rl_method* m);
+int cddt_save(rl_method* m, const char* path);
+int cddt_load(rl_method* m, const char* path);
+int cddt_index_build(rl_method* m, bool force_on = false);
 // rl_sort.cu
 int spatial_order(rl_method* m, const float* d_ins, int n, const int** d_perm);
 void sort_free(rl_method* m);

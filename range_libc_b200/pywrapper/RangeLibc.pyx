@@ -45,6 +45,9 @@ cdef extern from "rangelib_b200.h":
     int rl_method_create(int kind, const rl_map* m, float max_range, unsigned td, int device, rl_method** out)
     void rl_method_destroy(rl_method* m)
     int rl_method_prune(rl_method* m, float max_range)
+    int rl_method_save_cddt(rl_method* m, const char* path)
+    int rl_method_create_from_cddt(const rl_map* m, const char* path, int device, rl_method** out)
+    int rl_method_get_params(const rl_method* m, float* max_range, unsigned* td, int* pruned)
     int rl_calc_range(rl_method* m, float x, float y, float heading, float* out)
     int rl_calc_range_many(rl_method* m, const float* ins, float* outs, int n)
     int rl_numpy_calc_range(rl_method* m, const float* ins, float* outs, int n)
@@ -290,12 +293,38 @@ cdef class PyRayMarchingGPU(_Method):
         self._create(RL_RM, Map, max_range, 0)
 
 
+_pending_checkpoint = None  # set by PyCDDTCast.load around the construction of the object it returns
+
+
 cdef class PyCDDTCast(_Method):
     def __cinit__(self, PyOMap Map, float max_range, unsigned int theta_disc):
-        self._create(RL_CDDT, Map, max_range, theta_disc)
+        cdef float mr = 0
+        if _pending_checkpoint is not None:
+            self.ptr = NULL
+            _ck(rl_method_create_from_cddt(Map.ptr, _pending_checkpoint, -1, &self.ptr))
+            _ck(rl_method_get_params(self.ptr, &mr, NULL, NULL))
+            self.max_range = mr
+        else:
+            self._create(RL_CDDT, Map, max_range, theta_disc)
 
     cpdef prune(self, float max_range=-1.0):
         _ck(rl_method_prune(self.ptr, self.max_range if max_range < 0.0 else max_range))
+
+    def save(self, path):
+        """Binary checkpoint of the (possibly pruned) table (extension: the reference only dumps YAML / JSON text for
+        its viewer, RangeLib.h:1652-1735, and has no loader).  Load with PyCDDTCast.load(omap, path)."""
+        p = path if isinstance(path, bytes) else str(path).encode()
+        _ck(rl_method_save_cddt(self.ptr, p))
+
+    @staticmethod
+    def load(PyOMap Map, path):
+        """A CDDT / PCDDT method for `Map` from a checkpoint written by save(): no rebuild, no prune."""
+        global _pending_checkpoint
+        _pending_checkpoint = path if isinstance(path, bytes) else str(path).encode()
+        try:
+            return PyCDDTCast(Map, 0.0, 0)
+        finally:
+            _pending_checkpoint = None
 
 
 cdef class PyGiantLUTCast(_Method):

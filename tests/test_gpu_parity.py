@@ -110,9 +110,15 @@ def test_fresh_queries_vs_oracle(kn):
     W, H = occ.shape
     q = wl.random_queries(W, H, 200000, seed=2024)
     out = np.empty(len(q), np.float32)
-    make(kn, occ).calc_range_many_grid(q, out)
+    meth = make(kn, occ)
+    meth.calc_range_many_grid(q, out)
     ref = port.Oracle(KINDS[kn], occ, MR, TD, threads=8).calc_range_many(q)
     assert_bit_equal(out, ref, kn)
+    if kn in ("cddt", "pcddt"):  # the query index built for tables larger than L2, forced on this small one
+        meth.set_spatial_sort(2)
+        out2 = np.empty_like(out)
+        meth.calc_range_many_grid(q, out2)
+        assert_bit_equal(out2, ref, kn + " through the query index")
 
 
 def test_device_pointers_and_stream():
@@ -707,6 +713,10 @@ def test_fuzz_small_random_maps_all_kinds():
             out = np.empty(len(q), np.float32)
             meth.calc_range_many_grid(q, out)
             assert_bit_equal(out, o.calc_range_many(q), what + " grid")
+            if kn in ("cddt", "pcddt") and it % 2:  # odd iterations: everything below through the CDDT query index
+                meth.set_spatial_sort(2)
+                meth.calc_range_many_grid(q, out)
+                assert_bit_equal(out, o.calc_range_many(q), what + " grid, query index")
             meth.calc_range_many(qw, out)
             assert_bit_equal(out, o.numpy_calc_range(qw), what + " world")
             fan = np.empty(len(parts) * len(angles), np.float32)

@@ -202,10 +202,10 @@ def test_multi_gpu_torchrun_all_gather_paths():
 
 
 @pytest.mark.parametrize("name,pruned", [("gigantic_map", False), ("huge_map", True)])
-def test_c3_bin_ordered_cddt_queries(name, pruned):
-    """C3: big CDDT / PCDDT batches on tables larger than L2 are partitioned by bin range (histogram + scan + scatter +
-    cast of the partitioned records).  Only the processing order changes: the first 20 000 results reproduce the reference digests, the
-    whole batch equals a launch in caller order, in grid, world and repeat-angles form."""
+def test_c3_indexed_cddt_queries(name, pruned):
+    """C3: CDDT / PCDDT tables larger than L2 are queried through the L2-resident index (per-bin record + one skip entry
+    per 64-byte block of zero points).  Only the memory accesses change: the first 20 000 results reproduce the
+    reference digests, the whole batch equals the direct search, in grid, world and repeat-angles form."""
     import json
     import torch
     from helpers import GOLD
@@ -223,21 +223,19 @@ def test_c3_bin_ordered_cddt_queries(name, pruned):
     q[30001] = [-1e9, 3e9, 0.5]
     qd = torch.from_numpy(q).cuda()
     out = torch.empty(len(q), dtype=torch.float32, device="cuda")
-    l0 = rl.kernel_launches()
+    mem_indexed = cd.memory()
     cd.calc_range_many_grid(qd, out)
     cd.synchronize()
-    assert rl.kernel_launches() - l0 >= 4, "the bin-ordered path did not run"
     got = out.cpu().numpy()
     key = "pcddt_ranges_sha256" if pruned else "cddt_ranges_sha256"
     assert hashlib.sha256(got[:20000].tobytes()).hexdigest() == dig[key]
     assert got[30000] == MR and got[30001] == MR
     cd.set_spatial_sort(False)
+    assert cd.memory() < mem_indexed - (1 << 20), "the query index was not in use"
     out2 = torch.empty_like(out)
-    l0 = rl.kernel_launches()
     cd.calc_range_many_grid(qd, out2)
     cd.synchronize()
-    assert rl.kernel_launches() - l0 == 1
-    assert_bit_equal(got, out2.cpu().numpy(), "%s bin-ordered vs caller-ordered, grid" % name)
+    assert_bit_equal(got, out2.cpu().numpy(), "%s indexed vs direct search, grid" % name)
     # world-frame batch and lidar fans
     qw = torch.from_numpy(wl.grid_to_world(q[:1 << 19], world[0], world[2], world[3], world[1])).cuda()
     angles = torch.from_numpy(wl.lidar_angles(16)).cuda()
@@ -250,5 +248,78 @@ def test_c3_bin_ordered_cddt_queries(name, pruned):
         cd.calc_range_repeat_angles(qw[:32768].contiguous(), angles, b)
         cd.synchronize()
         res[sort] = (a.cpu().numpy(), b.cpu().numpy())
-    assert_bit_equal(res[True][0], res[False][0], "%s bin-ordered vs caller-ordered, world" % name)
-    assert_bit_equal(res[True][1], res[False][1], "%s bin-ordered vs caller-ordered, repeat angles" % name)
+    assert_bit_equal(res[True][0], res[False][0], "%s indexed vs direct search, world" % name)
+    assert_bit_equal(res[True][1], res[False][1], "%s indexed vs direct search, repeat angles" % name)
+
+
+def test_cddt_checkpoint_roundtrip(tmp_path):
+    """a built and pruned table is saved as a binary checkpoint and loaded without rebuild: identical CSR
+    arrays and ranges (both bindings); a checkpoint does not load onto another map."""
+    occ = wl.load_map("basement_hallways_5cm")
+    W, H = occ.shape
+    omap = omap_of(occ)
+    world = (0.05, 0.3, -3.0, 2.0, float(np.float32(np.sin(0.3))), float(np.float32(np.cos(0.3))))
+    omap.set_world(*world)
+    q = wl.grid_to_world(wl.random_queries(W, H, 100000, seed=5), world[0], world[2], world[3], world[1])
+    for pruned in (False, True):
+        cd = rl.PyCDDTCast(omap, MR, TD)
+        if pruned:
+            cd.prune()
+        path = str(tmp_path / ("t%d.rlcddt" % pruned))
+        cd.save(path)
+        l0 = rl.kernel_launches()
+        ld = rl.PyCDDTCast.load(omap, path)
+        assert rl.kernel_launches() - l0 <= 2, "loading a checkpoint must not rebuild the table"  # occupancy tiles only
+        assert (ld.max_range, ld.theta_disc, ld.pruned) == (MR, TD, pruned)
+        for a, b in zip(cd.table(), ld.table()):
+            assert_bit_equal(a, b, "checkpointed table")
+        want, got = np.empty(len(q), np.float32), np.empty(len(q), np.float32)
+        cd.calc_range_many(q, want)
+        ld.calc_range_many(q, got)
+        assert_bit_equal(got, want, "ranges from the loaded table (pruned=%s)" % pruned)
+        sys.path.insert(0, os.path.join(ROOT, "range_libc_b200", "pywrapper"))
+        import range_libc as cy
+        cmap = cy.PyOMap(np.ascontiguousarray(occ.T.astype(bool)))
+        cmap.set_world(*world)
+        cl = cy.PyCDDTCast.load(cmap, path)
+        got2 = np.empty(len(q), np.float32)
+        cl.calc_range_many(q, got2)
+        assert_bit_equal(got2, want, "ranges from the loaded table, Cython binding")
+        cy.PyCDDTCast(cmap, MR, TD).save(str(tmp_path / "cy.rlcddt"))
+    other = omap_of(wl.load_map("basement_hallways_10cm"))
+    with pytest.raises(rl.RangeLibError):
+        rl.PyCDDTCast.load(other, path)
+    occ2 = occ.copy()
+    occ2[600, 600] ^= 1
+    with pytest.raises(rl.RangeLibError):
+        rl.PyCDDTCast.load(omap_of(occ2), path)
+
+
+@pytest.mark.parametrize("name", ["basement_hallways_10cm", "basement_fixed_rectangle", "small.map"])
+def test_distance_transform_both_forms(name):
+    """The distance transform is built by the integer form of the Felzenszwalb-Huttenlocher recurrence (sides <= 16384;
+    its first pass as nearest-set-bit queries for columns <= 4096 cells, switched off here with RL_EDT_DIRECT_PASS1=0)
+    every scanline cut into independently built segments, RL_EDT_SEGMENTS)
+    or by the double-precision form (larger maps; forced here with RL_EDT_EXACT_DIV=1): all bit-equal to the oracle's,
+    also on a map without any obstacle in some columns / rows and on one with none at all."""
+    occ = wl.load_map(name)
+    variants = [occ]
+    sparse = np.zeros_like(occ)
+    sparse[occ.shape[0] // 3, occ.shape[1] // 2] = 1      # one obstacle: most columns are all-free (FLT_MAX after pass 1)
+    variants.append(sparse)
+    first = np.zeros_like(occ)
+    first[0, :] = 1                                        # obstacles in element 0 of every pass-1... and pass-2 scanline
+    first[:, 0] = 1
+    variants.append(first)
+    variants.append(np.zeros_like(occ))                    # no obstacle at all
+    for o in variants:
+        want = port.edt(o)
+        for env in ({}, {"RL_EDT_DIRECT_PASS1": "0"}, {"RL_EDT_SEGMENTS": "1"}, {"RL_EDT_DIRECT_PASS1": "0", "RL_EDT_SEGMENTS": "3"},
+                    {"RL_EDT_EXACT_DIV": "1"}):
+            os.environ.update(env)
+            try:
+                got = rl.PyRayMarchingGPU(omap_of(o), MR).distance_transform()
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+            assert_bit_equal(got, want, "distance transform of %s (%s, %d obstacles)" % (name, env, int(o.sum())))
