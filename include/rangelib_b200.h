@@ -194,6 +194,22 @@ int rl_calc_range_repeat_angles_eval_sensor_model_sharded(rl_method* m, const fl
                                                           const float* obs, double* weights_all, int64_t offset,
                                                           int num_particles, int num_angles, int64_t n_total);
 
+/* ---- particle-filter steps either side of the sensor update ------------------------
+ * NOT part of the reference: range_libc ends at the weights (RangeLib.h:558-612); these are the steps its downstream
+ * user (the mit-racecar particle_filter MCL loop named in the reference's README) runs on the host between two sensor
+ * updates, offered here so that particles and weights can stay on the device.  The handle supplies device, stream and
+ * scratch only (any kind).  Pointers: HOST (blocking) or DEVICE (asynchronous), not mixed.  Exact definitions:
+ * range_libc_b200/csrc/rl_pf.cu; checker: oracle/pf_oracle.py. */
+/* w_i <- pow(w_i, inv_squash) (skipped when inv_squash == 1), then w_i <- w_i / sum(w).  *sum_out (HOST, may be NULL;
+ * non-NULL makes the call blocking) receives the sum of the squashed weights. */
+int rl_pf_normalize_weights(rl_method* m, double* weights, int n, double inv_squash, double* sum_out);
+/* systematic (low-variance) resampling with one uniform draw u0 in [0, 1): out_particles[j] = particles[i_j], i_j the
+ * first i whose fixed-point (2^-40) cumulative weight exceeds ((u0 + j) / n) * total.  Order-independent, bit-exact. */
+int rl_pf_resample(rl_method* m, const float* particles, const double* weights, float* out_particles, int n, double u0);
+/* odometry step of n planar poses (x, y, theta), in place: x += cos(theta) dx - sin(theta) dy (+ noise[3i]),
+ * y += sin(theta) dx + cos(theta) dy (+ noise[3i+1]), theta += dtheta (+ noise[3i+2]); noise: n x 3 floats or NULL. */
+int rl_pf_motion_update(rl_method* m, float* particles, int n, float dx, float dy, float dtheta, const float* noise);
+
 /* ---- table-level access for parity tests ---------------------------------------------------- */
 /* the occupancy bytes resident on the device, x-major out[x*H+y] (after dynamic updates / device ingest). out: HOST */
 int rl_debug_get_occ(rl_method* m, uint8_t* out);

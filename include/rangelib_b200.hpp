@@ -71,6 +71,18 @@ class RangeMethod {
                                         float max_angle) {
     check(rl_calc_range_many_radial_optimized(h_, ins, outs, num_particles, num_rays, min_angle, max_angle));
   }
+  // extensions (not in RangeLib.h): particle-filter steps either side of the sensor update, see rangelib_b200.h
+  double normalize_weights(double* weights, int n, double inv_squash = 1.0) {
+    double sum = 0.0;
+    check(rl_pf_normalize_weights(h_, weights, n, inv_squash, &sum));
+    return sum;
+  }
+  void resample(const float* particles, const double* weights, float* out_particles, int n, double u0) {
+    check(rl_pf_resample(h_, particles, weights, out_particles, n, u0));
+  }
+  void motion_update(float* particles, int n, float dx, float dy, float dtheta, const float* noise = nullptr) {
+    check(rl_pf_motion_update(h_, particles, n, dx, dy, dtheta, noise));
+  }
   float maxRange() const { return max_range_; }
   long long memory() const { return (long long)rl_method_memory(h_); }
   rl_method* handle() { return h_; }
@@ -110,6 +122,8 @@ class CDDTCast : public RangeMethod {
  public:
   CDDTCast(const OMap& m, float mr, unsigned int td) : RangeMethod(RL_CDDT, m, mr, td) {}
   void prune(float max_range) { check(rl_method_prune(h_, max_range)); }
+  // extension: binary checkpoint of the (pruned) table; load with rl_method_create_from_cddt (rangelib_b200.h)
+  void save(const char* path) { check(rl_method_save_cddt(h_, path)); }
 };
 
 class GiantLUTCast : public RangeMethod {

@@ -164,6 +164,37 @@ class _RangeMethod:
             raise ValueError("shape mismatch")
         check(lib().rl_calc_range_repeat_angles_eval_sensor_model(self._h, pi, pa, pb, pw, si[0], sa[0]))
 
+    # -- particle-filter steps either side of the sensor update (not in the reference; rl_pf.cu) ----------
+    def normalize_weights(self, weights, inv_squash=1.0, want_sum=False):
+        """weights f64[N] in place: w <- pow(w, inv_squash) / sum.  Returns the sum of the squashed weights when
+        want_sum (blocking)."""
+        pw, sw = _buf(weights, np.float64, 1, "weights")
+        s = C.c_double()
+        check(lib().rl_pf_normalize_weights(self._h, pw, sw[0], float(inv_squash), C.byref(s) if want_sum else None))
+        return s.value if want_sum else None
+
+    def resample(self, particles, weights, out_particles, u0):
+        """Systematic resampling of particles f32[N,3] by (normalised) weights f64[N] into out_particles, one uniform
+        draw u0 in [0, 1)."""
+        pp, sp = _buf(particles, np.float32, 2, "particles")
+        pw, sw = _buf(weights, np.float64, 1, "weights")
+        po, so = _buf(out_particles, np.float32, 2, "out_particles")
+        if sp[1] != 3 or so[1] != 3 or sw[0] < sp[0] or so[0] < sp[0]:
+            raise ValueError("shape mismatch")
+        check(lib().rl_pf_resample(self._h, pp, pw, po, sp[0], float(u0)))
+
+    def motion_update(self, particles, dx, dy, dtheta, noise=None):
+        """Odometry step of particles f32[N,3] in place; noise f32[N,3] or None."""
+        pp, sp = _buf(particles, np.float32, 2, "particles")
+        pn = None
+        if noise is not None:
+            pn, sn = _buf(noise, np.float32, 2, "noise")
+            if sn[0] < sp[0] or sn[1] != 3:
+                raise ValueError("noise must be [N,3]")
+        if sp[1] != 3:
+            raise ValueError("particles must be [N,3]")
+        check(lib().rl_pf_motion_update(self._h, pp, sp[0], float(dx), float(dy), float(dtheta), pn))
+
     def calc_range_many_radial_optimized(self, num_rays, min_angle, max_angle, ins, outs):
         """RangeLibc.pyx:274-276 (argument order as there).  outs f32[N*num_rays], updated in place: beams the
         reference does not write keep their previous content."""

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librangelib_b200.so")
-SOURCES = ["rl_abi.cu", "rl_occ.cu", "rl_edt.cu", "rl_cddt.cu", "rl_cast.cu", "rl_sort.cu"]
+SOURCES = ["rl_abi.cu", "rl_occ.cu", "rl_edt.cu", "rl_cddt.cu", "rl_cast.cu", "rl_sort.cu", "rl_pf.cu"]
 HEADERS = ["rl_internal.cuh", "rl_math.cuh", os.path.join(ROOT, "include", "rangelib_b200.h")]
 
 NVCC_FLAGS = [

@@ -33,6 +33,9 @@ SIGNATURES = {
     "rl_method_save_cddt": (_i, [_vp, C.c_char_p]),
     "rl_method_get_params": (_i, [_vp, C.POINTER(_f), C.POINTER(C.c_uint), C.POINTER(_i)]),
     "rl_method_create_from_cddt": (_i, [_vp, C.c_char_p, _i, C.POINTER(_vp)]),
+    "rl_pf_normalize_weights": (_i, [_vp, _vp, _i, C.c_double, C.POINTER(C.c_double)]),
+    "rl_pf_resample": (_i, [_vp, _vp, _vp, _vp, _i, C.c_double]),
+    "rl_pf_motion_update": (_i, [_vp, _vp, _i, _f, _f, _f, _vp]),
     "rl_method_set_stream": (_i, [_vp, _vp]),
     "rl_method_use_own_stream": (_i, [_vp]),
     "rl_method_synchronize": (_i, [_vp]),

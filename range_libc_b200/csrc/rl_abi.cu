@@ -346,6 +346,7 @@ static void free_method(rl_method* m) {
   dg.bind(m->device);
   cddt_free(m);
   sort_free(m);
+  pf_free(m);
   cudaFree(m->d_occ);
   cudaFree(m->d_bits_t);
   cudaFree(m->d_dt);
@@ -791,6 +792,71 @@ int rl_eval_sensor_model(rl_method* m, const float* obs, const float* ranges, do
 int rl_calc_range_repeat_angles_eval_sensor_model(rl_method* m, const float* ins, const float* angles,
                                                   const float* obs, double* weights, int n, int M) {
   return run_cast(m, MODE_FUSED, ins, angles, obs, nullptr, weights, n, M);
+}
+
+// ---- particle-filter steps either side of the sensor update (rl_pf.cu; SURVEY 8 f4, not in the reference) ----
+int rl_pf_normalize_weights(rl_method* m, double* weights, int n, double inv_squash, double* sum_out) {
+  DeviceGuard dg;
+  int rc = dg.bind(m);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && !weights)) {
+    set_error("rl_pf_normalize_weights: bad arguments");
+    return RL_E_INVALID;
+  }
+  if (n == 0) {
+    if (sum_out) *sum_out = 0.0;
+    return RL_OK;
+  }
+  Marshal ms(m);
+  const int iw = ms.add_inout(weights, sizeof(double) * (size_t)n);
+  rc = ms.prepare();
+  if (rc) return rc;
+  rc = pf_normalize(m, (double*)ms.dev(iw), n, inv_squash, sum_out);
+  if (rc) return rc;
+  return ms.finish();
+}
+
+int rl_pf_resample(rl_method* m, const float* particles, const double* weights, float* out_particles, int n, double u0) {
+  DeviceGuard dg;
+  int rc = dg.bind(m);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!particles || !weights || !out_particles)) || !(u0 >= 0.0 && u0 < 1.0)) {
+    set_error("rl_pf_resample: bad arguments (u0 must be in [0, 1))");
+    return RL_E_INVALID;
+  }
+  if (n == 0) return RL_OK;
+  Marshal ms(m);
+  const int ip = ms.add(particles, sizeof(float) * 3 * (size_t)n, false);
+  const int iw = ms.add(weights, sizeof(double) * (size_t)n, false);
+  const int io = ms.add(out_particles, sizeof(float) * 3 * (size_t)n, true);
+  rc = ms.prepare();
+  if (rc) return rc;
+  if (ms.dev(ip) == ms.dev(io)) {
+    set_error("rl_pf_resample: in-place resampling is not supported");
+    return RL_E_INVALID;
+  }
+  rc = pf_resample(m, (const float*)ms.dev(ip), (const double*)ms.dev(iw), (float*)ms.dev(io), n, u0);
+  if (rc) return rc;
+  return ms.finish();
+}
+
+int rl_pf_motion_update(rl_method* m, float* particles, int n, float dx, float dy, float dtheta, const float* noise) {
+  DeviceGuard dg;
+  int rc = dg.bind(m);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && !particles)) {
+    set_error("rl_pf_motion_update: bad arguments");
+    return RL_E_INVALID;
+  }
+  if (n == 0) return RL_OK;
+  Marshal ms(m);
+  const int ip = ms.add_inout(particles, sizeof(float) * 3 * (size_t)n);
+  const int in_ = noise ? ms.add(noise, sizeof(float) * 3 * (size_t)n, false) : -1;
+  rc = ms.prepare();
+  if (rc) return rc;
+  rc = pf_motion(m, (float*)ms.dev(ip), n, dx, dy, dtheta, noise ? (const float*)ms.dev(in_) : nullptr);
+  if (rc) return rc;
+  return ms.finish();
 }
 
 // RangeMethod::calc_range_many_radial_optimized RangeLib.h:616-676 (loop constants :635-645 restated with the

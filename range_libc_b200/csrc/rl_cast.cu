@@ -290,11 +290,15 @@ __device__ __forceinline__ float rm_march_coop(const MapView& mv, float max_rang
 // code -- no branch, no reconvergence point -- and rm_result classifies the ray afterwards from t alone.
 struct RmSlot {
   float x0, y0, dx, dy, t;
+  unsigned cell = 0;  // index of the last distance-map cell read (always inside the map)
   int id;
   bool busy;   // the slot holds a ray (marching, or ended and not yet written out)
   bool alive;  // ... and it is still marching
 };
 
+#ifndef RL_RM_PRED_LOAD
+#define RL_RM_PRED_LOAD 0  // 1: idle lanes re-read their last cell (17-instruction step); measured slower, see rm_step_pred
+#endif
 template <bool COND_LOAD>
 __device__ __forceinline__ void rm_step_pred(const float* __restrict__ dt, unsigned W, unsigned H, float max_range,
                                              RmSlot& r) {
@@ -308,7 +312,18 @@ __device__ __forceinline__ void rm_step_pred(const float* __restrict__ dt, unsig
   if (COND_LOAD) {
     if (go) d = __ldg(dt + ((unsigned)px * H + (unsigned)py));
   } else {
+#if RL_RM_PRED_LOAD
+    // Measured and dropped (round 2): lanes that are not marching re-read the last cell they visited -- `cell = go ? new
+    // : cell` is one predicated IMAD and ptxas then forms the address with one IMAD.WIDE, 17 instructions per step
+    // instead of 19 (IMAD, SEL, LEA, LEA.HI.X).  Slower everywhere (RM random 38.4 -> 35.6 G rays/s, 100000 x 60 fused
+    // 23.5 -> 18.2, judged C2 step 23.6 -> 25.5 us): 32 idle lanes now touch up to 32 different lines per request where
+    // they all hit cell 0's line, and L1 tag lookups are what these kernels run out of.  (A predicated load in inline
+    // PTX is turned back into a branch by ptxas.)
+    r.cell = go ? (unsigned)px * H + (unsigned)py : r.cell;
+    d = __ldg(dt + r.cell);
+#else
     d = __ldg(dt + (go ? (unsigned)px * H + (unsigned)py : 0u));
+#endif
   }
   const bool adv = go && !(d <= 0.0f);
   const float tn = fadd(r.t, fmaxf(fmul(d, 0.999f), 1.0f));
@@ -1193,8 +1208,11 @@ bl_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
 // shuffles, instead of RL_QB per lane in shared memory: the kernel then uses no shared memory at all and the
 // whole 256 KB of the SM serves as L1 for the distance-map gathers (which are what bounds it: ncu shows the
 // L1 -> crossbar miss-request interface busy 85 % of the active cycles, one missing sector per clock per SM).
+#ifndef RL_RM_PERSIST_MINB
+#define RL_RM_PERSIST_MINB 6
+#endif
 template <int MODE, int SLOTS, bool COND_LOAD, bool PARK_REGS>
-__global__ void __launch_bounds__(256, SLOTS == 1 ? 6 : 4)
+__global__ void __launch_bounds__(256, SLOTS == 1 ? RL_RM_PERSIST_MINB : 4)
 rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __restrict__ ins,
                   const float* __restrict__ angles, float* __restrict__ outs, long long total, int M, int chunk,
                   int burst_pairs) {
@@ -1469,10 +1487,26 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
       return RL_E_STATE;
     }
     const int chunk = min(M, 2048);
-    const int ppb = max(1, min(threads / max(M, 1), 32));
+    // Deep launches of many-beam particles (BASELINE config 5: 10^6 x 1080): a CTA handles one particle at a time and
+    // stops at a barrier while one thread forms the 1080-term product.  Measured alternatives, all bit-exact, none
+    // faster (round 2, 8192^2 map / 5 cm map 20000 x 1080, G rays/s): 256-thread CTAs 26.5 / 32.2 (kept);
+    // 128-thread CTAs (RL_FUSED_DEEP_THREADS=128) 23.6 / 33.3; 64-thread 16.8 / 23.5; one warp per particle with the
+    // product slipped into the next batch's march, no barrier at all, 25.3 / 31.4 (ncu: issue slots 70 % busy instead
+    // of 60 %, but 12 % more instructions -- the launch is bound by instruction issue either way); producer warps +
+    // one consumer warp streaming rays through shared-memory rings 8.1 / 7.0.
+    static const int deep_threads = getenv("RL_FUSED_DEEP_THREADS") ? atoi(getenv("RL_FUSED_DEEP_THREADS")) : 256;
+    const bool many_beams = mv.coop_threshold == 0 && M >= 512 && (deep_threads == 64 || deep_threads == 128);
+    const int fthreads = many_beams ? deep_threads : threads;
+    const int ppb = max(1, min(fthreads / max(M, 1), 32));
     const int groups = (n + ppb - 1) / ppb;
-    const int grid = max(1, min(groups, sm_count() * 8));
     const size_t smem = (size_t)ppb * chunk * sizeof(double);
+    int per_sm = 8;  // resident CTAs per SM: the grid-stride loop wants exactly one wave
+    if (many_beams &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<KIND, false>, fthreads, smem) != cudaSuccess) {
+      cudaGetLastError();
+      per_sm = 8;
+    }
+    const int grid = max(1, min(groups, sm_count() * max(per_sm, 1)));
     PeerOut po{};
     if (peers) po = *peers;
     // big clouds on structures larger than L2: process the particles tile by tile (rl_sort.cu)
@@ -1499,9 +1533,9 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
           mv, m->xf, m->sensor_view(), m->max_range, ins, angles, obs, weights, n, M, ppb2, chunk, po, perm,
           RL_RM_BURST_PAIRS);
     } else {
-      fused_kernel<KIND, false><<<grid, threads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range, ins,
-                                                                    angles, obs, weights, n, M, ppb, chunk, po,
-                                                                    NoBeamParams{}, perm);
+      fused_kernel<KIND, false><<<grid, fthreads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range, ins,
+                                                                     angles, obs, weights, n, M, ppb, chunk, po,
+                                                                     NoBeamParams{}, perm);
     }
   } else {
     const long long total = (mode == MODE_ANGLES) ? (long long)n * M : (long long)n;
@@ -1531,7 +1565,7 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     static const int rm_persist_env = getenv("RL_RM_PERSIST") ? atoi(getenv("RL_RM_PERSIST")) : -1;
     static const int rm_burst_pairs = getenv("RL_RM_BURST_PAIRS") ? max(1, atoi(getenv("RL_RM_BURST_PAIRS"))) : RL_RM_BURST_PAIRS;
     const int variant = rm_persist_env >= 0 ? rm_persist_env : m->persist;
-    const long long resident_warps = (long long)sm_count() * (variant == 4 ? 32 : 48);
+    const long long resident_warps = (long long)sm_count() * (variant == 4 ? 32 : 8 * RL_RM_PERSIST_MINB);
     if (KIND == RL_RM && m->max_range > 0.0f && total >= resident_warps * 64 && variant) {
       long long per_warp = (total + resident_warps - 1) / resident_warps;
       const int chunk = (int)min((long long)1 << 20, ((per_warp + 31) / 32) * 32);

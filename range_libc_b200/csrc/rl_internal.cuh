@@ -195,6 +195,9 @@ struct rl_method {
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   int sort_cap = 0;
+  // particle-filter steps (rl_pf.cu): reduction result, fixed-point weights / prefix sums, cub scratch
+  void* d_pf = nullptr;
+  size_t pf_bytes = 0;
   // calc_range_many_radial_optimized: beam-angle table of the last call
   float* d_radial = nullptr;
   int radial_cap = 0, radial_rays = -1, radial_count = 0;
@@ -242,6 +245,11 @@ int cddt_index_build(rl_method* m, bool force_on = false);
 // rl_sort.cu
 int spatial_order(rl_method* m, const float* d_ins, int n, const int** d_perm);
 void sort_free(rl_method* m);
+// rl_pf.cu (device pointers)
+int pf_normalize(rl_method* m, double* d_w, int n, double inv_squash, double* h_sum);
+int pf_resample(rl_method* m, const float* d_particles, const double* d_w, float* d_out, int n, double u0);
+int pf_motion(rl_method* m, float* d_particles, int n, float dx, float dy, float dth, const float* d_noise);
+void pf_free(rl_method* m);
 // rl_cast.cu -- the batched query kernels (all kinds, all modes)
 int launch_cast(rl_method* m, int mode, const float* d_ins, const float* d_angles, const float* d_obs, float* d_outs,
                 double* d_weights, int n, int num_angles, const PeerOut* peers = nullptr);

@@ -48,6 +48,9 @@ cdef extern from "rangelib_b200.h":
     int rl_method_save_cddt(rl_method* m, const char* path)
     int rl_method_create_from_cddt(const rl_map* m, const char* path, int device, rl_method** out)
     int rl_method_get_params(const rl_method* m, float* max_range, unsigned* td, int* pruned)
+    int rl_pf_normalize_weights(rl_method* m, double* weights, int n, double inv_squash, double* sum_out)
+    int rl_pf_resample(rl_method* m, const float* particles, const double* weights, float* out_particles, int n, double u0)
+    int rl_pf_motion_update(rl_method* m, float* particles, int n, float dx, float dy, float dtheta, const float* noise)
     int rl_calc_range(rl_method* m, float x, float y, float heading, float* out)
     int rl_calc_range_many(rl_method* m, const float* ins, float* outs, int n)
     int rl_numpy_calc_range(rl_method* m, const float* ins, float* outs, int n)
@@ -213,6 +216,39 @@ cdef class _Method:
         if ins.shape[1] != 3 or outs.shape[0] < ins.shape[0] * angles.shape[0]:
             raise ValueError("outs must hold N*M floats")
         _ck(rl_numpy_calc_range_angles(self.ptr, &ins[0, 0], &angles[0], &outs[0], <int>ins.shape[0], <int>angles.shape[0]))
+
+    # particle-filter steps either side of the sensor update (extensions: not in the reference; rl_pf.cu)
+    def normalize_weights(self, double[::1] weights, double inv_squash=1.0):
+        """weights in place: w <- pow(w, inv_squash) / sum; returns the sum of the squashed weights."""
+        cdef double total = 0.0
+        if weights.shape[0] == 0:
+            return 0.0
+        _ck(rl_pf_normalize_weights(self.ptr, &weights[0], <int>weights.shape[0], inv_squash, &total))
+        return total
+
+    def resample(self, float[:, ::1] particles, double[::1] weights, float[:, ::1] out_particles, double u0):
+        """systematic resampling by (normalised) weights with one uniform draw u0 in [0, 1)"""
+        if particles.shape[0] == 0:
+            return
+        if particles.shape[1] != 3 or out_particles.shape[1] != 3 or weights.shape[0] < particles.shape[0] \
+                or out_particles.shape[0] < particles.shape[0]:
+            raise ValueError("shape mismatch")
+        _ck(rl_pf_resample(self.ptr, &particles[0, 0], &weights[0], &out_particles[0, 0], <int>particles.shape[0], u0))
+
+    def motion_update(self, float[:, ::1] particles, float dx, float dy, float dtheta, noise=None):
+        """odometry step in place; noise f32[N,3] or None"""
+        cdef float[:, ::1] nz
+        if particles.shape[0] == 0:
+            return
+        if particles.shape[1] != 3:
+            raise ValueError("particles must be [N,3]")
+        if noise is None:
+            _ck(rl_pf_motion_update(self.ptr, &particles[0, 0], <int>particles.shape[0], dx, dy, dtheta, NULL))
+        else:
+            nz = noise
+            if nz.shape[0] < particles.shape[0] or nz.shape[1] != 3:
+                raise ValueError("noise must be [N,3]")
+            _ck(rl_pf_motion_update(self.ptr, &particles[0, 0], <int>particles.shape[0], dx, dy, dtheta, &nz[0, 0]))
 
     cpdef calc_range_repeat_angles_eval_sensor_model(self, float[:, ::1] ins, float[::1] angles, float[::1] obs,
                                                      double[::1] weights):
