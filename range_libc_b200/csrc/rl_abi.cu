@@ -723,7 +723,7 @@ int64_t rl_method_memory(const rl_method* m) {
   int64_t bytes = (int64_t)m->W * m->H + (int64_t)m->tiles8_x() * m->tiles8_y() * 8;
   if (m->kind == RL_RM || m->kind == RL_GLT) bytes += (int64_t)m->dt_elems() * 4;
   if (m->kind == RL_GLT) bytes += (int64_t)m->W * m->H * m->td * 2;
-  if (m->kind == RL_CDDT || m->kind == RL_PCDDT) bytes += m->nvalues * 4 + (m->nbins + 1) * 8 + (int64_t)m->td * 16 + ((m->use_index && m->spatial_sort) ? m->nbins * 16 + m->nskip * 4 : 0);
+  if (m->kind == RL_CDDT || m->kind == RL_PCDDT) bytes += m->nvalues * 4 + (m->nbins + 1) * 8 + (int64_t)m->td * 16 + ((m->use_index && m->spatial_sort) ? m->nbins * 16 + m->nskip * 2 : 0);
   return bytes;
 }
 

@@ -601,25 +601,34 @@ __device__ __forceinline__ void cddt_discretize(const CddtView& cv, float theta,
 // Search of one bin through the query index (rl_cddt.cu: cddt_index_build).  Returns the absolute position in
 // values[] of the first element of the bin [o0, o0 + size) that does NOT satisfy the bin-monotone predicate
 //   le ? v <= lx : v < lx        (o0 + size when all satisfy it)
-// which is o0 + the `lo` the plain bisections below end with.  skip[k] == values[16 k], so the blocks k0+1 .. k1 that
-// START inside the bin are bisected through skip[] (L2-resident), and the one 64-byte aligned block that holds the
+// which is o0 + the `lo` the plain bisections below end with.  skip[k] is the 16-bit monotone code of values[16 k]
+// (rl_internal.cuh: cddt_code), so the blocks k0+1 .. k1 that START inside the bin are bisected through skip[]
+// (L2-resident; a probe whose code equals the query's reads the value itself), and the one 64-byte aligned block that holds the
 // boundary is read with 16-byte loads and counted branch-free; elements of the block that belong to the neighbouring
 // bins are masked out by position.
 #ifndef RL_CDDT_BLOCK_UNROLL
 #define RL_CDDT_BLOCK_UNROLL 4  // 16-byte loads of the block in flight at once (4: all; 1: one at a time, 12 registers less)
 #endif
 __device__ __forceinline__ unsigned cddt_search_indexed(const CddtView& cv, unsigned o0, unsigned size, float lx,
-                                                        bool le) {
+                                                        bool le, float first, float last) {
   const unsigned o1 = o0 + size;  // size >= 1
   const unsigned k0 = o0 >> 4, k1 = (o1 - 1) >> 4;
-  const float* __restrict__ S = cv.skip + k0 + 1;
+  const uint16_t* __restrict__ S = cv.skip + k0 + 1;
   int lo = 0, n = (int)(k1 - k0);
-  while (n > 0) {
-    const int half = n >> 1;
-    const float v = __ldg(S + lo + half);
-    const bool go_right = le ? !(lx < v) : (v < lx);
-    lo = go_right ? lo + half + 1 : lo;
-    n = go_right ? n - half - 1 : half;
+  if (n > 0) {
+    const float scale = cddt_code_scale(first, last);
+    const unsigned cq = cddt_code(lx, first, scale);  // first <= lx <= last here
+    while (n > 0) {
+      const int half = n >> 1;
+      const unsigned c = __ldg(S + lo + half);
+      bool go_right = c < cq;  // code order implies value order; equal codes: compare the values
+      if (c == cq) {
+        const float v = __ldg(cv.values + ((size_t)(k0 + 1 + lo + half) << 4));
+        go_right = le ? !(lx < v) : (v < lx);
+      }
+      lo = go_right ? lo + half + 1 : lo;
+      n = go_right ? n - half - 1 : half;
+    }
   }
   const unsigned kk = k0 + (unsigned)lo;  // the last block whose first element satisfies the predicate, or k0
   const float4* __restrict__ blk = reinterpret_cast<const float4*>(cv.values + ((size_t)kk << 4));
@@ -683,7 +692,7 @@ __device__ __forceinline__ float cddt_cast_indexed(const MapView& mv, const Cddt
     le = (int)size - 1 > RL_BINARY_SEARCH_THRESHOLD;
   }
   if ((word >> ((cx & 7) * 8 + (cy & 7))) & 1ULL) return 0.0f;  // map.grid[x][y] :1413 / :1475
-  const unsigned p = cddt_search_indexed(cv, o0, size, lx, le);
+  const unsigned p = cddt_search_indexed(cv, o0, size, lx, le, first, last);
   return flipped ? fsub(lx, __ldg(cv.values + p - 1)) : fsub(__ldg(cv.values + p), lx);
 }
 
@@ -1461,6 +1470,12 @@ static int sm_count() {
   return c;
 }
 
+// CTA size of SMALL fused launches (the ones that fit the chip about once and run the cooperative tail)
+static int small_fused_threads() {
+  static const int v = getenv("RL_FUSED_SMALL_THREADS") ? atoi(getenv("RL_FUSED_SMALL_THREADS")) : 256;
+  return (v == 64 || v == 128 || v == 192) ? v : 256;
+}
+
 static int block_burst_pairs() {  // tuning knob of rm_march_block (RL_BLOCK_BURST_PAIRS), default RL_BLOCK_BURST / 2
   static const int v = getenv("RL_BLOCK_BURST_PAIRS") ? max(1, atoi(getenv("RL_BLOCK_BURST_PAIRS"))) : RL_BLOCK_BURST / 2;
   return v;
@@ -1496,7 +1511,7 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     // one consumer warp streaming rays through shared-memory rings 8.1 / 7.0.
     static const int deep_threads = getenv("RL_FUSED_DEEP_THREADS") ? atoi(getenv("RL_FUSED_DEEP_THREADS")) : 256;
     const bool many_beams = mv.coop_threshold == 0 && M >= 512 && (deep_threads == 64 || deep_threads == 128);
-    const int fthreads = many_beams ? deep_threads : threads;
+    const int fthreads = many_beams ? deep_threads : (mv.coop_threshold != 0 ? small_fused_threads() : threads);
     const int ppb = max(1, min(fthreads / max(M, 1), 32));
     const int groups = (n + ppb - 1) / ppb;
     const size_t smem = (size_t)ppb * chunk * sizeof(double);
@@ -1506,7 +1521,7 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
       cudaGetLastError();
       per_sm = 8;
     }
-    const int grid = max(1, min(groups, sm_count() * max(per_sm, 1)));
+    const int grid = max(1, min(groups, sm_count() * max(per_sm, 1) * (many_beams ? 1 : 256 / fthreads)));
     PeerOut po{};
     if (peers) po = *peers;
     // big clouds on structures larger than L2: process the particles tile by tile (rl_sort.cu)
@@ -1633,13 +1648,14 @@ template <int KIND>
 static int launch_fused_beam_params_kind(rl_method* m, const float* ins, const BeamParams& beams, double* weights, int n,
                                          int M) {
   MapView mv = m->map_view();
-  const int threads = 256;
+  int threads = 256;
   if ((long long)n * M > 2LL * sm_count() * 7 * threads) mv.coop_threshold = 0;  // as in launch_cast_kind
+  else threads = small_fused_threads();
   mv.block_burst_pairs = block_burst_pairs();
   const int chunk = min(M, 2048);
   const int ppb = max(1, min(threads / max(M, 1), 32));
   const int groups = (n + ppb - 1) / ppb;
-  const int grid = max(1, min(groups, sm_count() * 8));
+  const int grid = max(1, min(groups, sm_count() * 8 * 256 / threads));
   const size_t smem = (size_t)ppb * chunk * sizeof(double);
   fused_kernel<KIND, true><<<grid, threads, smem, m->stream>>>(mv, m->cddt_view(), m->xf, m->sensor_view(), m->max_range,
                                                                ins, nullptr, nullptr, weights, n, M, ppb, chunk,

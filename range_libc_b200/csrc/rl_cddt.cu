@@ -302,9 +302,11 @@ inline int slices_to_fill(unsigned td) {  // the reference iterates a < td / 2.0
 // stream through L2 once, but the partition itself cost as much as it saved (12.3 and 13.6 G rays/s).  The index
 // makes the part of the search that decides WHERE to look small enough to live in L2:
 //   meta[bin]  one 16-byte record: offset, size, first and last value of the bin            (13 MB on C3)
-//   skip[k]    values[16 k]: the first value of every 64-byte aligned block of values[]     (40 MB on C3, 15 MB pruned)
-// A query reads its record (the early exits need nothing else), bisects the skip entries of the blocks that start
-// inside its bin (L2), and then reads the ONE aligned 64-byte block of values[] that holds its answer with four
+//   skip[k]    a 16-bit monotone position code (cddt_code) of values[16 k], the first value of every 64-byte aligned
+//              block of values[], relative to the bin that holds it                         (20 MB on C3, 7 MB pruned)
+// A query reads its record (the early exits need nothing else), bisects the skip codes of the blocks that start
+// inside its bin (L2; a code equal to the query's own code decides nothing and that probe reads the value itself --
+// 0.5-pixel resolution on gigantic_map, so it is rare), and then reads the ONE aligned 64-byte block of values[] that holds its answer with four
 // 16-byte loads -- one DRAM access instead of nine.  The search returns the same element as before: its predicate is
 // monotone along a bin, so "count the blocks whose first element satisfies it, then the elements inside the last such
 // block" is the same bisection split in two (cddt_search_indexed, rl_cast.cu).
@@ -323,9 +325,19 @@ __global__ void index_meta_kernel(const int64_t* __restrict__ off, const float* 
   mt.last = size ? vals[o0 + size - 1] : 0.0f;
   meta[b] = mt;
 }
-__global__ void index_skip_kernel(const float* __restrict__ vals, int64_t nskip, float* __restrict__ skip) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < nskip) skip[k] = vals[k * RL_CDDT_BLOCK];
+// one warp per bin: codes of the blocks that start inside the bin (after its first element; the block that holds the
+// bin's first element is never probed, see cddt_search_indexed)
+__global__ void index_skip_kernel(const CddtBinMeta* __restrict__ meta, const float* __restrict__ vals, int64_t nbins,
+                                  uint16_t* __restrict__ skip) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= nbins) return;
+  const CddtBinMeta mt = meta[b];
+  if (mt.size == 0) return;
+  const unsigned k0 = mt.off >> 4, k1 = (mt.off + mt.size - 1) >> 4;
+  const float scale = cddt_code_scale(mt.first, mt.last);
+  for (unsigned k = k0 + 1 + lane; k <= k1; k += 32)
+    skip[k] = (uint16_t)cddt_code(vals[(size_t)k * RL_CDDT_BLOCK], mt.first, scale);
 }
 }  // namespace
 
@@ -345,9 +357,10 @@ int cddt_index_build(rl_method* m, bool force_on) {
   cudaStream_t st = m->stream;
   const int64_t nskip = (int64_t)(cddt_values_alloc(m->nvalues) / RL_CDDT_BLOCK);
   RL_CUDA(cudaMalloc(&m->d_meta, sizeof(CddtBinMeta) * (size_t)nbins));
-  RL_CUDA(cudaMalloc(&m->d_skip, sizeof(float) * (size_t)nskip));
+  RL_CUDA(cudaMalloc(&m->d_skip, sizeof(uint16_t) * (size_t)nskip));
+  RL_CUDA(cudaMemsetAsync(m->d_skip, 0, sizeof(uint16_t) * (size_t)nskip, st));
   index_meta_kernel<<<blocks_for(nbins, 256), 256, 0, st>>>(m->d_offsets, m->d_values, nbins, m->d_meta);
-  index_skip_kernel<<<blocks_for(nskip, 256), 256, 0, st>>>(m->d_values, nskip, m->d_skip);
+  index_skip_kernel<<<blocks_for(nbins * 32, 256), 256, 0, st>>>(m->d_meta, m->d_values, nbins, m->d_skip);
   count_launch(2);
   RL_CHECK_LAUNCH();
   RL_CUDA(cudaStreamSynchronize(st));

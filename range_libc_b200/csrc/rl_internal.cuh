@@ -80,6 +80,18 @@ struct __align__(16) CddtBinMeta {
 inline size_t cddt_values_alloc(int64_t nvalues) {
   return (((size_t)nvalues + RL_CDDT_BLOCK) / RL_CDDT_BLOCK + 1) * RL_CDDT_BLOCK;
 }
+#ifdef __CUDACC__
+// 16-bit position code of a zero point inside its bin [first, last]: MONOTONE non-decreasing in v (every operation
+// is: subtraction of a constant, multiplication by a non-negative constant, clamp, truncation), so for two values of
+// one bin  code(a) < code(b)  implies  a < b;  equal codes decide nothing and the caller compares the values.
+__device__ __forceinline__ float cddt_code_scale(float first, float last) {
+  return last > first ? __fdiv_rn(65535.0f, __fsub_rn(last, first)) : 0.0f;
+}
+__device__ __forceinline__ unsigned cddt_code(float v, float first, float scale) {
+  const float t = fminf(fmaxf(__fmul_rn(__fsub_rn(v, first), scale), 0.0f), 65535.0f);
+  return (unsigned)__float2int_rz(t);
+}
+#endif
 
 struct CddtView {
   unsigned td;
@@ -93,7 +105,7 @@ struct CddtView {
   float td_div_2pi;         // (float)(td / M_2PI)           RangeLib.h:976
   float twopi_div_td;       // (float)(M_2PI / (float)td)    RangeLib.h:977
   const CddtBinMeta* meta;  // [nbins] query index, or nullptr: search values[] directly
-  const float* skip;        // skip[k] = values[16 k]
+  const uint16_t* skip;     // skip[k] = cddt_code of values[16 k] relative to the bin that holds it
 };
 
 struct SensorView {
@@ -166,7 +178,7 @@ struct rl_method {
   float* d_values = nullptr;
   int64_t nbins = 0, nvalues = 0;
   rl::CddtBinMeta* d_meta = nullptr;  // query index over the table (rebuilt whenever the table changes)
-  float* d_skip = nullptr;
+  uint16_t* d_skip = nullptr;
   int64_t nskip = 0;
   bool use_index = false;  // queries go through the index (tables larger than L2; RL_CDDT_INDEX=0|1 overrides)
   std::vector<int> h_widths;
