@@ -856,6 +856,22 @@ __device__ __forceinline__ int sensor_index(float v, float kmax) {
 // kernels
 // ------------------------------------------------------------------------------------------
 
+// t / m and t % m for t < 2^22 * m, t < 2^24 (ray indices inside a chunk or a particle group) without the integer
+// division sequence (ncu source view, round 2: the 64-bit `r / M` of the pose load was 12 % of all instructions issued by
+// the lidar-fan kernel).  rcp_m = 1 / m rounded towards zero; the truncated float product is the quotient or one
+// below it (both roundings go down, relative error < 2^-22), which one multiply-subtract and a compare settle.
+__device__ __forceinline__ float rcp_floor(unsigned m) { return __frcp_rz((float)m); }
+__device__ __forceinline__ void divmod_small(unsigned t, unsigned m, float rcp_m, unsigned* q, unsigned* r) {
+  unsigned qq = __float2uint_rz(__fmul_rz((float)t, rcp_m));
+  unsigned rr = t - qq * m;
+  if (rr >= m) {
+    ++qq;
+    rr -= m;
+  }
+  *q = qq;
+  *r = rr;
+}
+
 // resolves ray r of a batch into the pose handed to calc_range, per entry point
 template <int MODE>
 __device__ __forceinline__ void load_pose(const WorldXform& xf, const float* __restrict__ ins,
@@ -1004,14 +1020,17 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
     for (int c0 = 0; c0 < M; c0 += chunk) {
       const int cm = min(chunk, M - c0);
       const int rays = np * cm;
+      const float rcp_cm = rcp_floor((unsigned)cm);
       for (int k0 = 0; k0 < rays; k0 += blockDim.x) {  // block-uniform trip count
         const int k = k0 + threadIdx.x;
         const bool valid = k < rays;
         int p = 0, a = c0;
         float gx = 0.f, gy = 0.f, gth = 0.f;
         if (valid) {
-          p = k / cm;
-          a = c0 + (k - p * cm);
+          unsigned up, ua;
+          divmod_small((unsigned)k, (unsigned)cm, rcp_cm, &up, &ua);  // k < ppb * cm <= 65536
+          p = (int)up;
+          a = c0 + (int)ua;
           const size_t i = perm ? (size_t)__ldg(perm + p0 + p) : (size_t)(p0 + p);  // processing order only
           float x, y, th;
           world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
@@ -1130,29 +1149,41 @@ template <int MODE>
 __global__ void __launch_bounds__(256, 5)
 bl_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __restrict__ ins,
                   const float* __restrict__ angles, float* __restrict__ outs, long long total, int M, int chunk,
-                  int refill_at, int burst_len) {
+                  int refill_at, int burst_len, unsigned long long* __restrict__ work) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long begin = warp_global * chunk;
-  const long long end = min(begin + (long long)chunk, total);
-  if (begin >= end) return;
-  const int count = (int)(end - begin);
-  int next = 0;  // next ray of the chunk to hand out (warp-uniform)
+  // the warps claim pieces of `chunk` rays from a global cursor (see rm_persist_kernel): walks differ in length by two
+  // orders of magnitude, and with fixed slices 27 % of the resident warp slots idled (ncu, round 2)
+  long long begin = 0;
+  int count = 0, next = 0;  // current piece, next ray of it to hand out (warp-uniform)
+  bool exhausted = false;
   bool active = false;
-  int id = 0;
+  long long id = 0;
   BlState st;
   while (true) {
     const unsigned idle = __ballot_sync(FULL, !active);
     const int n_idle = __popc(idle);
+    if (next >= count && !exhausted && (n_idle >= refill_at || n_idle == 32)) {
+      unsigned long long b = 0;
+      if (lane == 0) b = atomicAdd(work, (unsigned long long)chunk);
+      b = __shfl_sync(FULL, b, 0);
+      next = 0;
+      if ((long long)b >= total) {
+        exhausted = true;
+        count = 0;
+      } else {
+        begin = (long long)b;
+        count = (int)min((long long)chunk, total - begin);
+      }
+    }
     if (next < count && (n_idle >= refill_at || n_idle == 32)) {
       const int rank = __popc(idle & ((1u << lane) - 1u));
       if (!active && next + rank < count) {
-        id = next + rank;
+        id = begin + next + rank;
         float gx, gy, gth, result;
-        load_pose<MODE>(xf, ins, angles, begin + id, M, &gx, &gy, &gth);
+        load_pose<MODE>(xf, ins, angles, id, M, &gx, &gy, &gth);
         if (bl_setup(mv, max_range, gx, gy, gth, st, &result)) {
-          outs[begin + id] = (MODE == MODE_GRID) ? result : fmul(result, xf.scale);
+          outs[id] = (MODE == MODE_GRID) ? result : fmul(result, xf.scale);
         } else {
           active = true;
         }
@@ -1169,7 +1200,7 @@ bl_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
         done = bl_step(mv, max_range, st, &result);
       } while (!done && --burst);
       if (done) {
-        outs[begin + id] = (MODE == MODE_GRID) ? result : fmul(result, xf.scale);
+        outs[id] = (MODE == MODE_GRID) ? result : fmul(result, xf.scale);
         active = false;
       }
     }
@@ -1197,7 +1228,7 @@ bl_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
 #define RL_FUSED_GROUP_RAYS 4096  // rays of one particle group in fused_rm_persist_kernel (2048: -8 %, 6144: -30 %)
 #endif
 #ifndef RL_RM_BURST_PAIRS
-#define RL_RM_BURST_PAIRS 3  // sphere-tracing steps per refill round = 2 * this
+#define RL_RM_BURST_PAIRS 4  // sphere-tracing steps per refill round = 2 * this (3 -> 4: lidar fans 39.5 -> 40.3 G rays/s, others unchanged)
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -1224,28 +1255,38 @@ template <int MODE, int SLOTS, bool COND_LOAD, bool PARK_REGS>
 __global__ void __launch_bounds__(256, SLOTS == 1 ? RL_RM_PERSIST_MINB : 4)
 rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __restrict__ ins,
                   const float* __restrict__ angles, float* __restrict__ outs, long long total, int M, int chunk,
-                  int burst_pairs) {
+                  int burst_pairs, unsigned long long* __restrict__ work) {
   constexpr int PARKED = PARK_REGS ? 32 : RL_QB * 32;  // rays per setup phase
   __shared__ float4 q_all[PARK_REGS ? 1 : 8 * RL_QB * 32];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float4* q = q_all + (PARK_REGS ? 0 : wib * (RL_QB * 32));
   float4 parked = make_float4(0.f, 0.f, 0.f, 0.f);
-  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
-  const long long begin = warp_global * chunk;
-  const long long end = min(begin + (long long)chunk, total);
-  if (begin >= end) return;
   const float out_scale = (MODE == MODE_GRID) ? 1.0f : xf.scale;
   const float* __restrict__ dt = mv.dt;
   const unsigned W = (unsigned)mv.W, H = (unsigned)mv.H;
 
-  const int count = (int)(end - begin);  // bookkeeping relative to `begin` (chunk <= 2^20)
+  // Work distribution (round 2): the warps CLAIM pieces of `chunk` rays from a global cursor instead of owning a fixed
+  // slice of the batch.  With fixed slices the launch ended when the slowest warp did, and ncu showed 59 % (lidar fans)
+  // / 70 % (random rays) of the warp slots occupied on average where 75 % were resident: warps that had finished their
+  // slice idled.  A warp asks for the next piece as soon as the rays of the current one have all been handed to lanes,
+  // so rays of two pieces march side by side and there is no per-piece tail.
+  long long begin = 0;  // first ray of the current piece
+  int count = 0;        // its length (bookkeeping relative to `begin`)
+  bool exhausted = false;
+  // lidar fans: ray begin + k is beam (a0 + k) % M of particle p0 + (a0 + k) / M -- one 64-bit division per piece
+  long long fan_p0 = 0;
+  unsigned fan_a0 = 0u;
+  const float fan_rcp = (MODE == MODE_ANGLES) ? rcp_floor((unsigned)M) : 0.0f;
+  const bool fan_fast = (MODE == MODE_ANGLES) && M < (1 << 22);
   int next_setup = 0, batch_base = 0, batch_n = 0, batch_pos = 0;
   RmSlot r[SLOTS];
+  long long rid[SLOTS];  // absolute index of the ray a slot holds
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     r[s].x0 = r[s].y0 = r[s].dx = r[s].dy = r[s].t = 0.f;
     r[s].id = 0;
+    rid[s] = 0;
     r[s].busy = r[s].alive = false;
   }
 
@@ -1258,6 +1299,23 @@ rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
       for (int pass = 0; pass < (PARK_REGS ? 2 : 1); ++pass) {
         const unsigned idle = __ballot_sync(FULL, !r[s].busy);
         if (idle) {
+          if (batch_pos == batch_n && next_setup >= count && !exhausted) {  // next piece (warp-uniform)
+            unsigned long long b = 0;
+            if (lane == 0) b = atomicAdd(work, (unsigned long long)chunk);
+            b = __shfl_sync(FULL, b, 0);
+            next_setup = 0;
+            if ((long long)b >= total) {
+              exhausted = true;
+              count = 0;
+            } else {
+              begin = (long long)b;
+              count = (int)min((long long)chunk, total - begin);
+              if (MODE == MODE_ANGLES) {
+                fan_p0 = begin / M;
+                fan_a0 = (unsigned)(begin - fan_p0 * M);
+              }
+            }
+          }
           if (batch_pos == batch_n && next_setup < count) {
             // ---- setup phase (warp-uniform branch): pose -> (x0, y0, cos, sin) for the next PARKED rays ----
             __syncwarp();
@@ -1266,7 +1324,18 @@ rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
             batch_pos = 0;
             for (int e = lane; e < batch_n; e += 32) {
               float gx, gy, gth;
-              load_pose<MODE>(xf, ins, angles, begin + batch_base + e, M, &gx, &gy, &gth);
+              if (MODE == MODE_ANGLES && fan_fast) {
+                unsigned dp, a;
+                divmod_small(fan_a0 + (unsigned)(batch_base + e), (unsigned)M, fan_rcp, &dp, &a);
+                const long long i = fan_p0 + dp;
+                float x, y, th;
+                world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
+                gx = y;  // calc_range(y, x, theta): RangeLib.h:518
+                gy = x;
+                gth = fsub(th, __ldg(angles + a));
+              } else {
+                load_pose<MODE>(xf, ins, angles, begin + batch_base + e, M, &gx, &gy, &gth);
+              }
               float sn = 0.f, cs = 0.f;
               const bool ok = finite3(gx, gy, gth);
               if (ok) rl_sincosf(gth, &sn, &cs);
@@ -1294,7 +1363,7 @@ rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
             if (take) {
               r[s].x0 = ray.x; r[s].y0 = ray.y; r[s].dx = ray.z; r[s].dy = ray.w;
               r[s].t = 0.0f;
-              r[s].id = batch_base + batch_pos + rank;
+              rid[s] = begin + batch_base + batch_pos + rank;
               r[s].busy = r[s].alive = true;
             }
             batch_pos += min(avail, __popc(idle));
@@ -1321,9 +1390,9 @@ rm_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
         if (MODE == MODE_GLT_BUILD) {
           // r = min(max_range, r); uint16 val = r * limits_div_max (RangeLib.h:1804-1806); xf.scale carries the factor
           const float rr = (result < max_range) ? result : max_range;
-          ((uint16_t*)outs)[begin + r[s].id] = (uint16_t)__float2int_rz(fmul(rr, xf.scale));
+          ((uint16_t*)outs)[rid[s]] = (uint16_t)__float2int_rz(fmul(rr, xf.scale));
         } else {
-          outs[begin + r[s].id] = (MODE == MODE_GRID) ? result : fmul(result, out_scale);
+          outs[rid[s]] = (MODE == MODE_GRID) ? result : fmul(result, out_scale);
         }
         r[s].busy = false;
       }
@@ -1361,6 +1430,7 @@ fused_rm_persist_kernel(MapView mv, WorldXform xf, SensorView sv, float max_rang
     for (int c0 = 0; c0 < M; c0 += chunk) {
       const int cm = min(chunk, M - c0);
       const int rays = np * cm;
+      const float rcp_cm = rcp_floor((unsigned)cm);
       if (threadIdx.x == 0) s_next = 0;
       __syncthreads();
       // ---- this warp's share of the group's rays: lane re-queuing as in rm_persist_kernel ----
@@ -1389,8 +1459,10 @@ fused_rm_persist_kernel(MapView mv, WorldXform xf, SensorView sv, float max_rang
                 batch_n = min(32, rays - b);
                 if (lane < batch_n) {
                   const int k = b + lane;
-                  const int p = k / cm;
-                  const int a = c0 + (k - p * cm);
+                  unsigned up, ua;
+                  divmod_small((unsigned)k, (unsigned)cm, rcp_cm, &up, &ua);  // k < group rays
+                  const int p = (int)up;
+                  const int a = c0 + (int)ua;
                   const size_t i = perm ? (size_t)__ldg(perm + p0 + p) : (size_t)(p0 + p);
                   float x, y, th;
                   world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
@@ -1429,7 +1501,9 @@ fused_rm_persist_kernel(MapView mv, WorldXform xf, SensorView sv, float max_rang
         if (r.busy && !r.alive) {
           const float d = rm_result(W, H, max_range, r);
           const int k = r.id;
-          const int a = c0 + (k - (k / cm) * cm);
+          unsigned up, ua;
+          divmod_small((unsigned)k, (unsigned)cm, rcp_cm, &up, &ua);
+          const int a = c0 + (int)ua;
           const int di = sensor_index(d, kmax);                                   // :602-603 (no scaling)
           const int ri = sensor_index(fmul(__ldg(obs + a), xf.inv_scale), kmax);  // :605-606
           vals[k] = __ldg(sv.table + (size_t)ri * sv.K + di);
@@ -1468,6 +1542,37 @@ static int sm_count() {
     if (c <= 0) c = 148;
   }
   return c;
+}
+
+// CTAs of a persistent kernel that are resident per SM (its grid must be exactly one wave: the launch bound only caps
+// the register count, what fits is decided by the count ptxas ended up with).  RL_PERSIST_CTAS overrides.
+template <class K>
+static int resident_ctas(K kernel, int threads, int fallback) {
+  static const int forced = getenv("RL_PERSIST_CTAS") ? atoi(getenv("RL_PERSIST_CTAS")) : 0;
+  if (forced > 0) return forced;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = fallback;
+  }
+  return n;
+}
+
+// the ray cursor of the persistent kernels, zeroed on the handle's stream before the launch that uses it
+static int fresh_work_cursor(rl_method* m, unsigned long long** out) {
+  if (!m->d_work) RL_CUDA(cudaMalloc(&m->d_work, sizeof(unsigned long long)));
+  RL_CUDA(cudaMemsetAsync(m->d_work, 0, sizeof(unsigned long long), m->stream));
+  *out = m->d_work;
+  return RL_OK;
+}
+// rays a warp of a persistent kernel claims at a time: RL_CLAIM_RAYS (default 128; measured 128 / 256 / 512 / 1024 on
+// 2^24 random rays 38.5 / 38.9 / 38.3 / 34.8 G rays/s, BL 2^22 rays 2.46 / 2.28 / 2.42 / -), less when the batch is
+// small, so that every resident warp gets about four pieces
+static int claim_rays(long long total, long long resident_warps) {
+  static const int v = getenv("RL_CLAIM_RAYS") ? atoi(getenv("RL_CLAIM_RAYS")) : 128;
+  static const int pieces = getenv("RL_CLAIM_PIECES") ? max(1, atoi(getenv("RL_CLAIM_PIECES"))) : 8;
+  const long long even = (total / (resident_warps * pieces) + 31) / 32 * 32;
+  return (int)max(32LL, min((long long)max(32, (v / 32) * 32), even));
 }
 
 // CTA size of SMALL fused launches (the ones that fit the chip about once and run the cooperative tail)
@@ -1557,19 +1662,24 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     // RM with enough rays to give every resident warp more than one ray per lane: persistent
     // warps with lane re-queuing.  (max_range <= 0 never enters the marching loop.)
     if (KIND == RL_BL && total >= (long long)sm_count() * 40 * 64 && m->persist) {
-      const long long rw = (long long)sm_count() * 40;
       static const int bl_refill = getenv("RL_BL_REFILL") ? atoi(getenv("RL_BL_REFILL")) : RL_BL_REFILL;
       static const int bl_burst = getenv("RL_BL_BURST") ? atoi(getenv("RL_BL_BURST")) : RL_BL_BURST;
-      long long per_warp = (total + rw - 1) / rw;
-      const int chunk = (int)min((long long)1 << 20, ((per_warp + 31) / 32) * 32);
-      const long long warps = (total + chunk - 1) / chunk;
+      const int ctas = mode == MODE_GRID    ? resident_ctas(bl_persist_kernel<MODE_GRID>, 256, 5)
+                       : mode == MODE_WORLD ? resident_ctas(bl_persist_kernel<MODE_WORLD>, 256, 5)
+                                            : resident_ctas(bl_persist_kernel<MODE_ANGLES>, 256, 5);
+      const long long rw = (long long)sm_count() * 8 * ctas;
+      const int chunk = claim_rays(total, rw);
+      const long long warps = min(rw, (total + chunk - 1) / chunk);
       const int grid = (int)((warps + 7) / 8);
+      unsigned long long* work = nullptr;
+      const int rcw = fresh_work_cursor(m, &work);
+      if (rcw) return rcw;
       if (mode == MODE_GRID)
-        bl_persist_kernel<MODE_GRID><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, bl_refill, bl_burst);
+        bl_persist_kernel<MODE_GRID><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, bl_refill, bl_burst, work);
       else if (mode == MODE_WORLD)
-        bl_persist_kernel<MODE_WORLD><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, bl_refill, bl_burst);
+        bl_persist_kernel<MODE_WORLD><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, bl_refill, bl_burst, work);
       else
-        bl_persist_kernel<MODE_ANGLES><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, bl_refill, bl_burst);
+        bl_persist_kernel<MODE_ANGLES><<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, bl_refill, bl_burst, work);
       count_launch();
       RL_CHECK_LAUNCH();
       return RL_OK;
@@ -1580,13 +1690,20 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     static const int rm_persist_env = getenv("RL_RM_PERSIST") ? atoi(getenv("RL_RM_PERSIST")) : -1;
     static const int rm_burst_pairs = getenv("RL_RM_BURST_PAIRS") ? max(1, atoi(getenv("RL_RM_BURST_PAIRS"))) : RL_RM_BURST_PAIRS;
     const int variant = rm_persist_env >= 0 ? rm_persist_env : m->persist;
-    const long long resident_warps = (long long)sm_count() * (variant == 4 ? 32 : 8 * RL_RM_PERSIST_MINB);
-    if (KIND == RL_RM && m->max_range > 0.0f && total >= resident_warps * 64 && variant) {
-      long long per_warp = (total + resident_warps - 1) / resident_warps;
-      const int chunk = (int)min((long long)1 << 20, ((per_warp + 31) / 32) * 32);
-      const long long warps = (total + chunk - 1) / chunk;
+    int rm_ctas = variant == 4 ? 4 : RL_RM_PERSIST_MINB;
+    if (KIND == RL_RM && variant == 1)
+      rm_ctas = mode == MODE_GRID    ? resident_ctas(rm_persist_kernel<MODE_GRID, 1, false, true>, 256, RL_RM_PERSIST_MINB)
+                : mode == MODE_WORLD ? resident_ctas(rm_persist_kernel<MODE_WORLD, 1, false, true>, 256, RL_RM_PERSIST_MINB)
+                                     : resident_ctas(rm_persist_kernel<MODE_ANGLES, 1, false, true>, 256, RL_RM_PERSIST_MINB);
+    const long long resident_warps = (long long)sm_count() * 8 * rm_ctas;
+    if (KIND == RL_RM && m->max_range > 0.0f && total >= (long long)sm_count() * 48 * 64 && variant) {
+      const int chunk = claim_rays(total, resident_warps);
+      const long long warps = min(resident_warps, (total + chunk - 1) / chunk);
       const int grid = (int)((warps + 7) / 8);
-#define RL_PERSIST_ARGS <<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, rm_burst_pairs)
+      unsigned long long* work = nullptr;
+      const int rcw = fresh_work_cursor(m, &work);
+      if (rcw) return rcw;
+#define RL_PERSIST_ARGS <<<grid, 256, 0, m->stream>>>(mv, m->xf, m->max_range, ins, angles, outs, total, M, chunk, rm_burst_pairs, work)
 #define RL_LAUNCH_PERSIST(MD)                                                      \
   do {                                                                             \
     if (variant == 2) rm_persist_kernel<MD, 1, true, true> RL_PERSIST_ARGS;        \
@@ -1734,14 +1851,17 @@ int glt_build(rl_method* m) {
     set_error("GiantLUTCast needs max_range > 0");
     return RL_E_INVALID;
   }
-  const long long resident_warps = (long long)sm_count() * 48;
-  long long per_warp = (total + resident_warps - 1) / resident_warps;
-  const int chunk = (int)min((long long)1 << 20, ((per_warp + 31) / 32) * 32);
-  const long long warps = (total + chunk - 1) / chunk;
+  const long long resident_warps =
+      (long long)sm_count() * 8 * resident_ctas(rm_persist_kernel<MODE_GLT_BUILD, 1, false, true>, 256, RL_RM_PERSIST_MINB);
+  const int chunk = claim_rays(total, resident_warps);
+  const long long warps = min(resident_warps, (total + chunk - 1) / chunk);
   const int grid = (int)((warps + 7) / 8);
+  unsigned long long* work = nullptr;
+  const int rcw = fresh_work_cursor(m, &work);
+  if (rcw) return rcw;
   rm_persist_kernel<MODE_GLT_BUILD, 1, false, true><<<grid, 256, 0, m->stream>>>(mv, xf, m->max_range, nullptr, nullptr,
                                                                         (float*)m->d_glt, total, (int)m->td, chunk,
-                                                                        RL_RM_BURST_PAIRS);
+                                                                        RL_RM_BURST_PAIRS, work);
   count_launch();
   RL_CHECK_LAUNCH();
   return RL_OK;

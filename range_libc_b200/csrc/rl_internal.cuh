@@ -194,6 +194,7 @@ struct rl_method {
   bool peers_ready = false;
   long long* d_epoch = nullptr;
   unsigned* d_counter = nullptr;
+  unsigned long long* d_work = nullptr;  // ray cursor of the persistent kernels (zeroed before each launch)
   long long host_epoch = 0;
   // staging for host-pointer calls
   void* d_stage = nullptr;
