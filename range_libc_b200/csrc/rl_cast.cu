@@ -1414,16 +1414,21 @@ __global__ void __launch_bounds__(256, 5)
 fused_rm_persist_kernel(MapView mv, WorldXform xf, SensorView sv, float max_range, const float* __restrict__ ins,
                         const float* __restrict__ angles, const float* __restrict__ obs,
                         double* __restrict__ weights, int N, int M, int ppb, int chunk, PeerOut peers,
-                        const int* __restrict__ perm, int burst_pairs) {
+                        const int* __restrict__ perm, int burst_pairs, unsigned long long* __restrict__ work) {
   extern __shared__ double vals[];
-  __shared__ int s_next;
+  __shared__ int s_next, s_group;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const float kmax = (float)((double)(float)sv.K - 1.0);
   const float* __restrict__ dt = mv.dt;
   const unsigned W = (unsigned)mv.W, H = (unsigned)mv.H;
   const int groups = (N + ppb - 1) / ppb;
-  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+  while (true) {
+    // the CTAs claim particle groups from a global cursor (groups differ in how long their rays are)
+    if (threadIdx.x == 0) s_group = (int)atomicAdd(work, 1ULL);
+    __syncthreads();
+    const int g = s_group;
+    if (g >= groups) break;
     const int p0 = g * ppb;
     const int np = min(ppb, N - p0);
     double w = 1.0;  // running product, owned by thread p < np
@@ -1547,11 +1552,11 @@ static int sm_count() {
 // CTAs of a persistent kernel that are resident per SM (its grid must be exactly one wave: the launch bound only caps
 // the register count, what fits is decided by the count ptxas ended up with).  RL_PERSIST_CTAS overrides.
 template <class K>
-static int resident_ctas(K kernel, int threads, int fallback) {
+static int resident_ctas(K kernel, int threads, int fallback, size_t dyn_smem = 0) {
   static const int forced = getenv("RL_PERSIST_CTAS") ? atoi(getenv("RL_PERSIST_CTAS")) : 0;
   if (forced > 0) return forced;
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n <= 0) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, dyn_smem) != cudaSuccess || n <= 0) {
     cudaGetLastError();
     n = fallback;
   }
@@ -1648,10 +1653,14 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
         6 * M <= group_rays) {
       const int ppb2 = max(1, min(group_rays / max(M, 1), 128));
       const int groups2 = (n + ppb2 - 1) / ppb2;
-      const int grid2 = max(1, min(groups2, sm_count() * 5));
+      const int grid2 = max(1, min(groups2, sm_count() * resident_ctas(fused_rm_persist_kernel, 256, 5,
+                                                                         (size_t)ppb2 * chunk * sizeof(double))));
+      unsigned long long* work = nullptr;
+      const int rcw = fresh_work_cursor(m, &work);
+      if (rcw) return rcw;
       fused_rm_persist_kernel<<<grid2, 256, (size_t)ppb2 * chunk * sizeof(double), m->stream>>>(
           mv, m->xf, m->sensor_view(), m->max_range, ins, angles, obs, weights, n, M, ppb2, chunk, po, perm,
-          RL_RM_BURST_PAIRS);
+          RL_RM_BURST_PAIRS, work);
     } else {
       fused_kernel<KIND, false><<<grid, fthreads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range, ins,
                                                                      angles, obs, weights, n, M, ppb, chunk, po,

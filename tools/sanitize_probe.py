@@ -65,3 +65,47 @@ cloud = wl.pf_particles_uniform(occ_big, 33000, seed=8)
 wc = np.empty(len(cloud), np.float64)
 rmb.calc_range_repeat_angles_eval_sensor_model(cloud, angles[:4].copy(), obs[:4].copy(), wc)
 print("late round-1 paths ok", float(fan.max()), float(wb.mean()), float(od.mean().item()), float(wc.mean()))
+
+# ---- round 2 additions --------------------------------------------------------------------------------------------
+import tempfile  # noqa: E402
+
+# CDDT query index (forced onto a small table) + cddt_batch_kernel (batches >= 65536 rays), plain and pruned
+cq = torch.from_numpy(wl.random_queries(W, H, 70000, seed=9)).cuda()
+co = torch.empty(len(cq), dtype=torch.float32, device="cuda")
+for pruned in (False, True):
+    ci = rl.PyCDDTCast(omap, 256.0, 24)
+    if pruned:
+        ci.prune()
+    ci.calc_range_many_grid(cq, co)      # direct search in the batch kernel
+    ci.set_spatial_sort(2)               # index: bin records + 16-bit skip codes
+    ci.calc_range_many_grid(cq, co)
+    ci.calc_range_many_grid(q, out)      # small batch through cast_kernel with the index
+    with tempfile.TemporaryDirectory() as d:  # binary checkpoint
+        ci.save(os.path.join(d, "t.rlcddt"))
+        cl = rl.PyCDDTCast.load(omap, os.path.join(d, "t.rlcddt"))
+        cl.calc_range_many_grid(q, out)
+    ci.synchronize()
+# distance transform variants: integer form with direct pass 1 / envelope pass 1 / segments, double-precision form
+for env in ({}, {"RL_EDT_DIRECT_PASS1": "0"}, {"RL_EDT_DIRECT_PASS1": "0", "RL_EDT_SEGMENTS": "3"}, {"RL_EDT_EXACT_DIV": "1"}):
+    os.environ.update(env)
+    rl.PyRayMarchingGPU(omap, 256.0).distance_transform()
+    for k in env:
+        os.environ.pop(k, None)
+# persistent kernels with claimed pieces: lidar fans (rm_persist_kernel<ANGLES>) and BL
+fp = torch.from_numpy(wl.pf_particles_uniform(occ, 12000, seed=10)).cuda()
+fa = torch.from_numpy(angles).cuda()
+fo = torch.empty(len(fp) * len(angles), dtype=torch.float32, device="cuda")
+rm2 = rl.PyRayMarchingGPU(omap, 256.0)
+rm2.calc_range_repeat_angles(fp, fa, fo)
+bl2 = rl.PyBresenhamsLine(omap, 256.0)
+bl2.calc_range_many_grid(qd, od)
+bl2.synchronize()
+# particle-filter steps
+pw = np.random.default_rng(11).uniform(0, 1, 5000)
+pp = wl.pf_particles_uniform(occ, 5000, seed=12)
+po = np.empty_like(pp)
+rm2.normalize_weights(pw, 1.0 / 2.2)
+rm2.resample(pp, pw, po, 0.3)
+rm2.motion_update(po, 0.2, 0.1, 0.05, np.zeros_like(po))
+rm2.synchronize()
+print("round-2 paths ok", float(co.mean().item()), float(fo.mean().item()), float(po.mean()))
