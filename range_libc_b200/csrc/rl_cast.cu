@@ -467,6 +467,8 @@ __device__ __forceinline__ bool occ_at(const MapView& mv, int x, int y) {  // OM
 //    any more and the result (max_range) is returned at once.
 struct BlState {
   float _x, _y, error, deltax, deltay, xstep, ystep, lo, hi, x0, y0;
+  float half_dx;         // smallest float e with 2 e >= deltax: `error * 2 >= deltax` is `error >= half_dx`
+  unsigned lim_a, lim_b; // map extent along the major / minor coordinate of the walk
   float stop_u;  // the walk is over (or has jumped its target) once xstep * _x >= stop_u
   int cur_tile;
   unsigned long long cur;
@@ -494,6 +496,12 @@ __device__ __forceinline__ bool bl_setup(const MapView& mv, float max_range, flo
   }
   st.deltax = fabsf(fsub(x1, x0));
   st.deltay = fabsf(fsub(y1, y0));
+  // 2 e is exact for every float e (no overflow at these magnitudes), so 2 e >= deltax  <=>  e >= deltax / 2 as real
+  // numbers  <=>  e >= the float just at or above deltax / 2
+  st.half_dx = __fmul_ru(st.deltax, 0.5f);
+  // not steep: _y indexes map x (< width), _x indexes map y (< height); steep: the other way round (:755/:761)
+  st.lim_a = st.steep ? (unsigned)mv.W : (unsigned)mv.H;
+  st.lim_b = st.steep ? (unsigned)mv.H : (unsigned)mv.W;
   st.error = 0.0f;
   st._x = st.x0 = x0;
   st._y = st.y0 = y0;
@@ -519,13 +527,11 @@ __device__ __forceinline__ bool bl_step(const MapView& mv, float max_range, BlSt
   *result = max_range;
   st._x = fadd(st._x, st.xstep);
   st.error = fadd(st.error, st.deltay);
-  if (fmul(st.error, 2.0f) >= st.deltax) {  // (double)error*2.0 >= (double)deltax: doubling is exact
+  if (st.error >= st.half_dx) {  // (double)error*2.0 >= (double)deltax (:750), see half_dx
     st._y = fadd(st._y, st.ystep);
     st.error = fsub(st.error, st.deltax);
   }
-  // not steep: _y indexes map x (< width), _x indexes map y (< height); steep: the other way round (:755/:761)
-  const unsigned lim_a = st.steep ? (unsigned)mv.W : (unsigned)mv.H;  // major coordinate _x
-  const unsigned lim_b = st.steep ? (unsigned)mv.H : (unsigned)mv.W;  // minor coordinate _y
+  const unsigned lim_a = st.lim_a, lim_b = st.lim_b;  // major coordinate _x, minor coordinate _y
   const int a = __float2int_rd(st._x), b = __float2int_rd(st._y);
   if ((unsigned)a < lim_a && (unsigned)b < lim_b) {
     const int cx = st.steep ? a : b, cy = st.steep ? b : a;  // map cell
@@ -534,7 +540,9 @@ __device__ __forceinline__ bool bl_step(const MapView& mv, float max_range, BlSt
       st.cur_tile = tile;
       st.cur = __ldg(mv.bits_t + tile);
     }
-    if ((st.cur >> ((cx & 7) * 8 + (cy & 7))) & 1ULL) {
+    unsigned occ_bit;  // bit (cx & 7) * 8 + (cy & 7) of the tile word, as a 32-bit test (SHF.R.U64 + LOP3 instead of a 64-bit compare)
+    asm("{\n\t.reg .u64 t;\n\tshr.u64 t, %1, %2;\n\tcvt.u32.u64 %0, t;\n\t}" : "=r"(occ_bit) : "l"(st.cur), "r"((cx & 7) * 8 + (cy & 7)));
+    if (occ_bit & 1u) {
       const float xd = fsub(st._x, st.x0), yd = fsub(st._y, st.y0);
       *result = __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
       return true;
