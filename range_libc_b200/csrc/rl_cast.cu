@@ -469,6 +469,8 @@ struct BlState {
   float _x, _y, error, deltax, deltay, xstep, ystep, lo, hi, x0, y0;
   float half_dx;         // smallest float e with 2 e >= deltax: `error * 2 >= deltax` is `error >= half_dx`
   unsigned lim_a, lim_b; // map extent along the major / minor coordinate of the walk
+  int target;            // the walk ends when trunc(_x) == target
+  unsigned swap_mask;    // 0 when steep (map cell = (a, b)), ~0 otherwise (map cell = (b, a)): one LOP3 per coordinate
   float stop_u;  // the walk is over (or has jumped its target) once xstep * _x >= stop_u
   int cur_tile;
   unsigned long long cur;
@@ -502,6 +504,7 @@ __device__ __forceinline__ bool bl_setup(const MapView& mv, float max_range, flo
   // not steep: _y indexes map x (< width), _x indexes map y (< height); steep: the other way round (:755/:761)
   st.lim_a = st.steep ? (unsigned)mv.W : (unsigned)mv.H;
   st.lim_b = st.steep ? (unsigned)mv.H : (unsigned)mv.W;
+  st.swap_mask = st.steep ? 0u : 0xffffffffu;
   st.error = 0.0f;
   st._x = st.x0 = x0;
   st._y = st.y0 = y0;
@@ -513,6 +516,7 @@ __device__ __forceinline__ bool bl_setup(const MapView& mv, float max_range, flo
   else if (target < 0) { st.lo = nextafterf((float)target - 1.0f, 0.0f); st.hi = nextafterf((float)target, 0.0f); }
   else { st.lo = nextafterf(-1.0f, 0.0f); st.hi = 1.0f; }
   if (target == INT_MIN || fabsf(x0) > 8388608.0f || fabsf(x1) > 8388608.0f) return true;  // far outside any map
+  st.target = target;
   st.cur_tile = -1;
   st.cur = 0;
   st.skipped = false;
@@ -523,8 +527,8 @@ __device__ __forceinline__ bool bl_setup(const MapView& mv, float max_range, flo
 }
 
 // one iteration of the walk (:745-767).  Returns true when the ray has ended.
+// *result is written only when the walk ends on an obstacle; the caller presets it to max_range
 __device__ __forceinline__ bool bl_step(const MapView& mv, float max_range, BlState& st, float* result) {
-  *result = max_range;
   st._x = fadd(st._x, st.xstep);
   st.error = fadd(st.error, st.deltay);
   if (st.error >= st.half_dx) {  // (double)error*2.0 >= (double)deltax (:750), see half_dx
@@ -534,7 +538,8 @@ __device__ __forceinline__ bool bl_step(const MapView& mv, float max_range, BlSt
   const unsigned lim_a = st.lim_a, lim_b = st.lim_b;  // major coordinate _x, minor coordinate _y
   const int a = __float2int_rd(st._x), b = __float2int_rd(st._y);
   if ((unsigned)a < lim_a && (unsigned)b < lim_b) {
-    const int cx = st.steep ? a : b, cy = st.steep ? b : a;  // map cell
+    const unsigned sm = st.swap_mask;  // map cell: (a, b) when steep, (b, a) otherwise -- a bitwise select each
+    const int cx = (int)(((unsigned)a & ~sm) | ((unsigned)b & sm)), cy = (int)(((unsigned)b & ~sm) | ((unsigned)a & sm));
     const int tile = (cx >> 3) * mv.tiles8_y + (cy >> 3);
     if (tile != st.cur_tile) {
       st.cur_tile = tile;
@@ -547,11 +552,14 @@ __device__ __forceinline__ bool bl_step(const MapView& mv, float max_range, BlSt
       *result = __fsqrt_rn(fadd(fmul(xd, xd), fmul(yd, yd)));
       return true;
     }
-  } else {
-    // left the map on the side the walk is heading to: nothing can be hit any more
-    if ((st.xstep > 0.0f) ? (a >= (int)lim_a) : (a < 0)) return true;
-    if ((st.ystep > 0.0f) ? (b >= (int)lim_b) : (b < 0)) return true;
+    // End of the walk, inside the map: _x >= 0 here, so trunc(_x) is the cell index a and the reference's loop test
+    // `(int)_x != (int)(x1 + xstep)` is one integer compare.  (a moves monotonically; if the float accumulation made it
+    // jump over the target -- see below -- it never equals it and the walk goes on, as the reference's does.)
+    return a == st.target;
   }
+  // outside the map: left on the side the walk is heading to -> nothing can be hit any more
+  if ((st.xstep > 0.0f) ? (a >= (int)lim_a) : (a < 0)) return true;
+  if ((st.ystep > 0.0f) ? (b >= (int)lim_b) : (b < 0)) return true;
   if (fmul(st.xstep, st._x) >= st.stop_u) {
     // Normally this is the end of the walk (trunc(_x) == target).  The reference's `_x += xstep` is a float
     // accumulation, though: when _x crosses a power of two with low fraction bits set the sum rounds and
@@ -569,6 +577,7 @@ __device__ __forceinline__ float bl_cast(const MapView& mv, float max_range, flo
   BlState st;
   float result;
   if (bl_setup(mv, max_range, x, y, heading, st, &result)) return result;
+  result = max_range;
   while (!bl_step(mv, max_range, st, &result)) {
   }
   return result;
@@ -1201,7 +1210,7 @@ bl_persist_kernel(MapView mv, WorldXform xf, float max_range, const float* __res
     }
     if (n_idle == 32) break;  // nothing left to hand out and nobody walking
     if (active) {
-      float result;
+      float result = max_range;
       bool done;
       int burst = burst_len;
       do {
