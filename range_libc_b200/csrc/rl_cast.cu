@@ -1105,6 +1105,156 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
   }
 }
 
+// Deep fused launches (many particle groups per CTA) of fused_kernel's kinds: the same work with the PRODUCT taken off
+// the marching warps' path.  fused_kernel ends every group with barrier / product / barrier: with 1080 beams the
+// product is a chain of 1080 dependent DMULs (~9 us) during which 255 threads wait (ncu, config 5: 9.8 warps per issued
+// instruction stalled at the barrier, issue slots 59 % busy).  Here a ninth warp owns the products: the eight marching
+// warps write a group's table values into one of two shared-memory buffers, ARRIVE at a named barrier and go on with the
+// next group; the product warp waits on that barrier, multiplies in beam order (lane p = particle p of the group),
+// stores the weights and frees the buffer through a second named barrier.  Barrier ids 1..4 (0 is __syncthreads):
+// FULL[b] = buffer b holds a whole group (256 arrive, 32 wait), FREE[b] = buffer b has been consumed (32 arrive, 256
+// wait, from the buffer's second use on).  Weights are bit-identical: same values, same order.
+// Measured (B200, profiles/r02/fused_overlap_r02.log): 20000 x 1080 on the 5 cm map 33.9 -> 37.6 G rays/s; on the
+// 8192^2 map (distance transform 268 MB > L2) 26.6 -> 24.9 -- nine warps per CTA leave room for 7 CTAs = 56 marching
+// warps per SM where fused_kernel has 64, and a launch that waits on L2 misses needs them -- so the launcher uses this
+// kernel only while the structure the rays read fits L2.  Also measured there and dropped: a barrier that keeps the
+// marching warps on the same group (no change), and rotating which warps get the partial last round of a group
+// (slower: a warp that keeps its beams looks the same way from particle to particle, and the particles are neighbours).
+// (immediate barrier ids: with an id in a register ptxas reserves all 16 named barriers for the CTA)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  switch (id) {
+    case 1: asm volatile("barrier.sync 1, %0;" ::"r"(count) : "memory"); break;
+    case 2: asm volatile("barrier.sync 2, %0;" ::"r"(count) : "memory"); break;
+    case 3: asm volatile("barrier.sync 3, %0;" ::"r"(count) : "memory"); break;
+    default: asm volatile("barrier.sync 4, %0;" ::"r"(count) : "memory"); break;
+  }
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  switch (id) {
+    case 1: asm volatile("barrier.arrive 1, %0;" ::"r"(count) : "memory"); break;
+    case 2: asm volatile("barrier.arrive 2, %0;" ::"r"(count) : "memory"); break;
+    case 3: asm volatile("barrier.arrive 3, %0;" ::"r"(count) : "memory"); break;
+    default: asm volatile("barrier.arrive 4, %0;" ::"r"(count) : "memory"); break;
+  }
+}
+#define RL_OVERLAP_MARCHERS 256
+#define RL_OVERLAP_THREADS (RL_OVERLAP_MARCHERS + 32)
+template <int KIND>
+__global__ void __launch_bounds__(RL_OVERLAP_THREADS, 7)
+fused_overlap_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_range,
+                     const float* __restrict__ ins, const float* __restrict__ angles, const float* __restrict__ obs,
+                     double* __restrict__ weights, int N, int M, int ppb, int chunk, PeerOut peers,
+                     const int* __restrict__ perm) {
+  extern __shared__ double vals[];  // two buffers of ppb * chunk doubles
+  const unsigned FULL = 0xffffffffu;
+  const float kmax = (float)((double)(float)sv.K - 1.0);
+  const int groups = (N + ppb - 1) / ppb;
+  const int buf_elems = ppb * chunk;
+  long long epoch = 0;
+  if (peers.sig) {  // signalled multi-GPU mode, as in fused_kernel
+    epoch = *(volatile long long*)peers.epoch + 1;
+    if (threadIdx.x < peers.n) {
+      volatile long long* mine = peers.flags[peers.rank];
+      while (mine[threadIdx.x] < epoch - 1) {
+      }
+    }
+    __syncthreads();
+  }
+  double* const* out_ptrs = (peers.sig && (epoch & 1)) ? peers.ptr1 : peers.ptr;
+  int use = 0;  // (group, chunk) iterations so far: buffer use & 1
+  if (threadIdx.x < RL_OVERLAP_MARCHERS) {
+    const float* __restrict__ dt = mv.dt;
+    const unsigned W = (unsigned)mv.W, H = (unsigned)mv.H;
+    for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+      const int p0 = g * ppb;
+      const int np = min(ppb, N - p0);
+      for (int c0 = 0; c0 < M; c0 += chunk, ++use) {
+        const int cm = min(chunk, M - c0);
+        const int rays = np * cm;
+        const float rcp_cm = rcp_floor((unsigned)cm);
+        double* v = vals + (use & 1) * buf_elems;
+        if (use >= 2) named_bar_sync(3 + (use & 1), RL_OVERLAP_THREADS);  // FREE[b]
+        for (int k0 = 0; k0 < rays; k0 += RL_OVERLAP_MARCHERS) {  // warp-uniform trip count
+          const int k = k0 + threadIdx.x;
+          const bool valid = k < rays;
+          int p = 0, a = c0;
+          float gx = 0.f, gy = 0.f, gth = 0.f;
+          if (valid) {
+            unsigned up, ua;
+            divmod_small((unsigned)k, (unsigned)cm, rcp_cm, &up, &ua);  // k < ppb * cm <= 65536
+            p = (int)up;
+            a = c0 + (int)ua;
+            const size_t i = perm ? (size_t)__ldg(perm + p0 + p) : (size_t)(p0 + p);  // processing order only
+            float x, y, th;
+            world_to_grid(xf, __ldg(ins + 3 * i), __ldg(ins + 3 * i + 1), __ldg(ins + 3 * i + 2), &x, &y, &th);
+            gx = y;
+            gy = x;
+            gth = fsub(th, __ldg(angles + a));
+          }
+          float d;
+          if (KIND == RL_RM) {
+            RmSlot r;
+            r.x0 = gx; r.y0 = gy; r.dx = 0.f; r.dy = 0.f;
+            r.t = 0.0f;
+            r.id = 0;
+            const bool ok = valid && rm_setup(max_range, gx, gy, gth, &r.dx, &r.dy);
+            r.busy = r.alive = ok;
+            while (__any_sync(FULL, r.alive)) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) rm_step_pred<false>(dt, W, H, max_range, r);
+            }
+            d = ok ? rm_result(W, H, max_range, r) : max_range;
+          } else {
+            d = valid ? cast_one<KIND>(mv, cv, max_range, gx, gy, gth) : 0.0f;
+          }
+          if (valid) {
+            const int di = sensor_index(d, kmax);                                   // :602-603 (no scaling)
+            const int ri = sensor_index(fmul(__ldg(obs + a), xf.inv_scale), kmax);  // :605-606
+            v[p * cm + (a - c0)] = __ldg(sv.table + (size_t)ri * sv.K + di);
+          }
+        }
+        named_bar_arrive(1 + (use & 1), RL_OVERLAP_THREADS);  // FULL[b]
+      }
+    }
+  } else {
+    const int lane = threadIdx.x & 31;
+    for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+      const int p0 = g * ppb;
+      const int np = min(ppb, N - p0);
+      double w = 1.0;  // running product, owned by lane p < np
+      for (int c0 = 0; c0 < M; c0 += chunk, ++use) {
+        const int cm = min(chunk, M - c0);
+        const double* v = vals + (use & 1) * buf_elems + lane * cm;
+        named_bar_sync(1 + (use & 1), RL_OVERLAP_THREADS);  // FULL[b]
+        if (lane < np)
+          for (int a = 0; a < cm; ++a) w = __dmul_rn(w, v[a]);  // reference order: beam ascending
+        named_bar_arrive(3 + (use & 1), RL_OVERLAP_THREADS);  // FREE[b]
+      }
+      if (lane < np) {
+        const size_t i = perm ? (size_t)__ldg(perm + p0 + lane) : (size_t)(p0 + lane);
+        if (peers.n == 0) {
+          weights[i] = w;
+        } else {  // all-gather by direct peer stores (NVLink): every GPU gets this rank's slice
+          for (int r = 0; r < peers.n; ++r) out_ptrs[r][peers.offset + i] = w;
+        }
+      }
+    }
+  }
+  if (peers.sig) {  // publish, as in fused_kernel
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned done = atomicAdd(peers.counter, 1u);
+      if (done == gridDim.x - 1) {
+        *peers.counter = 0u;
+        __threadfence_system();
+        *(volatile long long*)peers.epoch = epoch;
+        for (int r = 0; r < peers.n; ++r) ((volatile long long*)peers.flags[r])[peers.rank] = epoch;
+      }
+    }
+  }
+}
+
 // consumer-side wait of the signalled mode: returns (on the stream) once every rank's slice of the
 // latest epoch launched on this rank has arrived
 __global__ void peers_wait_kernel(PeerOut peers) {
@@ -1637,7 +1787,7 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     // of 60 %, but 12 % more instructions -- the launch is bound by instruction issue either way); producer warps +
     // one consumer warp streaming rays through shared-memory rings 8.1 / 7.0.
     static const int deep_threads = getenv("RL_FUSED_DEEP_THREADS") ? atoi(getenv("RL_FUSED_DEEP_THREADS")) : 256;
-    const bool many_beams = mv.coop_threshold == 0 && M >= 512 && (deep_threads == 64 || deep_threads == 128);
+    const bool many_beams = mv.coop_threshold == 0 && M >= 512 && deep_threads >= 32 && deep_threads < 256 && deep_threads % 8 == 0;
     const int fthreads = many_beams ? deep_threads : (mv.coop_threshold != 0 ? small_fused_threads() : threads);
     const int ppb = max(1, min(fthreads / max(M, 1), 32));
     const int groups = (n + ppb - 1) / ppb;
@@ -1679,9 +1829,25 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
           mv, m->xf, m->sensor_view(), m->max_range, ins, angles, obs, weights, n, M, ppb2, chunk, po, perm,
           RL_RM_BURST_PAIRS, work);
     } else {
-      fused_kernel<KIND, false><<<grid, fthreads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range, ins,
-                                                                     angles, obs, weights, n, M, ppb, chunk, po,
-                                                                     NoBeamParams{}, perm);
+      // deep launches: the product of a group overlaps the march of the next one (fused_overlap_kernel);
+      // RL_FUSED_OVERLAP=0 keeps fused_kernel (A/B)
+      static const bool overlap = !(getenv("RL_FUSED_OVERLAP") && atoi(getenv("RL_FUSED_OVERLAP")) == 0);
+      const int ppb_o = max(1, min(RL_OVERLAP_MARCHERS / max(M, 1), 32));
+      const int groups_o = (n + ppb_o - 1) / ppb_o;
+      const size_t smem_o = 2 * (size_t)ppb_o * chunk * sizeof(double);
+      const int grid_o = sm_count() * resident_ctas(fused_overlap_kernel<KIND>, RL_OVERLAP_THREADS, 7, smem_o);
+      // measured per kind (5 cm map, G rays/s, fused_kernel -> this kernel): RM 20000 x 1080 34.2 -> 37.8; CDDT
+      // 100000 x 60 29.4 -> 37.7, 50000 x 360 36.8 -> 51.5, 20000 x 1080 44.7 -> 59.0; BL 20000 x 60 1.35 -> 1.13 (its
+      // long walks are bound by issue slots and want the eighth CTA per SM more than the hidden product) -> not for BL
+      const bool fits_l2 = struct_bytes <= ((size_t)48 << 20) && (KIND != RL_CDDT || !cv.meta);
+      if (overlap && KIND != RL_BL && mv.coop_threshold == 0 && !many_beams && fits_l2 && groups_o >= 2 * grid_o) {
+        fused_overlap_kernel<KIND><<<grid_o, RL_OVERLAP_THREADS, smem_o, m->stream>>>(
+            mv, cv, m->xf, m->sensor_view(), m->max_range, ins, angles, obs, weights, n, M, ppb_o, chunk, po, perm);
+      } else {
+        fused_kernel<KIND, false><<<grid, fthreads, smem, m->stream>>>(mv, cv, m->xf, m->sensor_view(), m->max_range,
+                                                                       ins, angles, obs, weights, n, M, ppb, chunk, po,
+                                                                       NoBeamParams{}, perm);
+      }
     }
   } else {
     const long long total = (mode == MODE_ANGLES) ? (long long)n * M : (long long)n;

@@ -186,6 +186,38 @@ def test_c5_million_particles_1080_beams_8192():
     assert hashlib.sha256(got.tobytes()).hexdigest() == hashlib.sha256(w2.cpu().numpy().tobytes()).hexdigest()
 
 
+@pytest.mark.parametrize("kn,n,m_beams", [("rm", 2600, 1080), ("cddt", 12002, 60), ("pcddt", 9001, 97), ("rm", 3000, 700)])
+def test_deep_fused_updates_with_the_product_warp(kn, n, m_beams):
+    """Deep fused launches on a structure that fits L2 run fused_overlap_kernel (a ninth warp forms the products while
+    the others march the next group; named barriers, two value buffers): at least two groups per resident CTA, odd
+    group sizes, a partial last group.  Weights bit-equal to the oracle (RangeLib.h:558-612)."""
+    import torch
+    occ = wl.load_map("basement_hallways_10cm")
+    meth = method(kn, omap_of(occ))
+    table = wl.sensor_table(501)
+    meth.set_sensor_model(table)
+    parts = wl.pf_particles_uniform(occ, n, seed=21)
+    parts[7, 0] = np.nan          # a non-finite pose inside a group
+    parts[n - 1, :2] = -5000.0    # and one far outside the map, in the partial last group
+    angles = wl.lidar_angles(m_beams)
+    obs = np.clip(60 + 50 * np.sin(np.linspace(0, 6, m_beams)), 0, 500).astype(np.float32)
+    pd, ad, od = (torch.from_numpy(a).cuda() for a in (parts, angles, obs))
+    w = torch.full((n,), -1.0, dtype=torch.float64, device="cuda")
+    meth.calc_range_repeat_angles_eval_sensor_model(pd, ad, od, w)
+    meth.synchronize()
+    kind = {"rm": port.RM, "cddt": port.CDDT, "pcddt": port.CDDT}[kn]
+    ora = port.Oracle(kind, occ, MR, TD, threads=NTHREADS)
+    if kn == "pcddt":
+        ora.prune(MR)
+    ora.set_sensor_model(table)
+    # the oracle's BL / CDDT do not terminate on a non-finite pose (neither does the reference): compare the rest
+    keep = np.ones(n, bool)
+    keep[7] = False
+    want = ora.calc_range_repeat_angles_eval_sensor_model(np.ascontiguousarray(parts[keep]), angles, obs)
+    assert_bit_equal(w.cpu().numpy()[keep], want, "%s deep fused %d x %d vs oracle" % (kn, n, m_beams))
+    assert np.isfinite(w.cpu().numpy()[7])
+
+
 def test_multi_gpu_torchrun_all_gather_paths():
     """All gather paths (NCCL, peer stores, signalled, pipelined, host-pointer sharded call through both bindings)
     bit-equal to the oracle on every rank; needs two visible GPUs."""

@@ -109,3 +109,21 @@ rm2.resample(pp, pw, po, 0.3)
 rm2.motion_update(po, 0.2, 0.1, 0.05, np.zeros_like(po))
 rm2.synchronize()
 print("round-2 paths ok", float(co.mean().item()), float(fo.mean().item()), float(po.mean()))
+
+# round 2, second half: fused_overlap_kernel (ninth warp forms the products behind named barriers, two value buffers):
+# RM with many beams (one particle per group) and CDDT / PCDDT with 60 beams (four particles per group, partial last group)
+ma = wl.lidar_angles(700)
+mo = np.linspace(3, 200, 700).astype(np.float32)
+dp = wl.pf_particles_uniform(occ, 2300, seed=13)
+dw = np.empty(len(dp), np.float64)
+rm2.set_sensor_model(table)
+rm2.calc_range_repeat_angles_eval_sensor_model(dp, ma, mo, dw)
+cdp = wl.pf_particles_uniform(occ, 9003, seed=14)
+cw = np.empty(len(cdp), np.float64)
+for pruned in (False, True):
+    c2 = rl.PyCDDTCast(omap, 256.0, 24)
+    if pruned:
+        c2.prune()
+    c2.set_sensor_model(table)
+    c2.calc_range_repeat_angles_eval_sensor_model(cdp, angles, obs, cw)
+print("fused_overlap paths ok", float(dw.mean()), float(cw.mean()))
