@@ -1119,7 +1119,9 @@ fused_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, float max_ra
 // warps per SM where fused_kernel has 64, and a launch that waits on L2 misses needs them -- so the launcher uses this
 // kernel only while the structure the rays read fits L2.  Also measured there and dropped: a barrier that keeps the
 // marching warps on the same group (no change), and rotating which warps get the partial last round of a group
-// (slower: a warp that keeps its beams looks the same way from particle to particle, and the particles are neighbours).
+// (slower: a warp that keeps its beams looks the same way from particle to particle, and the particles are neighbours);
+// a 512-thread form for the big map (15 marching warps + the product warp, four CTAs = 60 marching warps per SM, 1 to 4
+// particles per group): 25.4 / 24.5 / 24.5 / 23.7 against fused_kernel's 25.9 -- hiding the product buys nothing there.
 // (immediate barrier ids: with an id in a register ptxas reserves all 16 named barriers for the CTA)
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   switch (id) {
