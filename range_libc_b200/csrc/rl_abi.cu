@@ -356,6 +356,8 @@ static void free_method(rl_method* m) {
   cudaFree(m->d_epoch);
   cudaFree(m->d_counter);
   cudaFree(m->d_work);
+  cudaFree(m->d_ts_ranges);
+  cudaFree(m->d_ts_poses);
   cudaFree(m->d_radial);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);

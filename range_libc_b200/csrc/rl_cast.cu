@@ -1257,6 +1257,131 @@ fused_overlap_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, floa
   }
 }
 
+// ---- deep fused updates as two kernels: cast to memory, then this one ------------------------------------------------
+// Measured on BASELINE config 5's map (8192^2, 200000 x 1080, tile-ordered particles): the lidar-fan cast alone runs at
+// 42.7 G rays/s where fused_kernel reaches 26.1 -- the fused launch pays for its per-particle structure (rounds of 256
+// rays that end with the slowest ray of the round, a barrier, the product), while the ranges cost 8 bytes of HBM
+// traffic per ray there and back, 5 % of the bandwidth at that rate.  Fusing is a latency device for launches that fit
+// the chip once; a deep update is the persistent lane-re-queuing cast into a scratch array followed by a streaming
+// evaluation (launch_fused_twostep).
+// eval_overlap_kernel: the sensor-model half (RangeLib.h:533-555 / :596-610) in fused_overlap_kernel's form -- eight
+// loader warps turn ranges into table values (coalesced range loads four deep, one table gather each) for a group of up
+// to 32 particles and a chunk of beams, the ninth warp multiplies, lane p = particle p, beam order, running product
+// carried over the chunks.  Rows of a value buffer are padded to an odd length (bank conflicts of the product warp).
+// range_scale = inv_world_scale for eval_sensor_model (:549-550), 1 for the fused semantics (:602-603, exact).
+__global__ void gather_poses_kernel(const float* __restrict__ ins, const int* __restrict__ perm, float* __restrict__ out,
+                                    int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t s = (size_t)__ldg(perm + i);
+  out[3 * (size_t)i] = __ldg(ins + 3 * s);
+  out[3 * (size_t)i + 1] = __ldg(ins + 3 * s + 1);
+  out[3 * (size_t)i + 2] = __ldg(ins + 3 * s + 2);
+}
+
+__global__ void __launch_bounds__(RL_OVERLAP_THREADS, 7)
+eval_overlap_kernel(SensorView sv, float obs_scale, float range_scale, const float* __restrict__ obs,
+                    const float* __restrict__ ranges, double* __restrict__ weights, int N, int M, int ppb, int chunk,
+                    long long out_base, const int* __restrict__ perm, PeerOut peers, int sig_first, int sig_last) {
+  extern __shared__ double vals[];  // two buffers of ppb * (chunk | 1) doubles
+  const float kmax = (float)((double)(float)sv.K - 1.0);
+  const int groups = (N + ppb - 1) / ppb;
+  const int stride = chunk | 1;
+  const int buf_elems = ppb * stride;
+  long long epoch = 0;
+  if (peers.sig) {  // signalled multi-GPU mode (fused_kernel): the first kernel of a step waits, the last publishes
+    epoch = *(volatile long long*)peers.epoch + 1;
+    if (sig_first) {
+      if (threadIdx.x < peers.n) {
+        volatile long long* mine = peers.flags[peers.rank];
+        while (mine[threadIdx.x] < epoch - 1) {
+        }
+      }
+      __syncthreads();
+    }
+  }
+  double* const* out_ptrs = (peers.sig && (epoch & 1)) ? peers.ptr1 : peers.ptr;
+  int use = 0;
+  if (threadIdx.x < RL_OVERLAP_MARCHERS) {
+    for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+      const int p0 = g * ppb;
+      const int np = min(ppb, N - p0);
+      for (int c0 = 0; c0 < M; c0 += chunk, ++use) {
+        const int cm = min(chunk, M - c0);
+        const int rays = np * cm;
+        const float rcp_cm = rcp_floor((unsigned)cm);
+        double* v = vals + (use & 1) * buf_elems;
+        if (use >= 2) named_bar_sync(3 + (use & 1), RL_OVERLAP_THREADS);  // FREE[b]
+        for (int k0 = threadIdx.x; k0 < rays; k0 += 4 * RL_OVERLAP_MARCHERS) {
+          float r[4];
+          int slot[4], a[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * RL_OVERLAP_MARCHERS;
+            slot[u] = -1;
+            a[u] = c0;
+            r[u] = 0.0f;
+            if (k < rays) {
+              unsigned up, uj;
+              divmod_small((unsigned)k, (unsigned)cm, rcp_cm, &up, &uj);  // k < ppb * cm <= 65536
+              a[u] = c0 + (int)uj;
+              slot[u] = (int)up * stride + (int)uj;
+              r[u] = __ldg(ranges + (size_t)(p0 + (int)up) * M + a[u]);
+            }
+          }
+          double t[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int di = sensor_index(fmul(r[u], range_scale), kmax);
+            const int ri = sensor_index(fmul(__ldg(obs + a[u]), obs_scale), kmax);
+            t[u] = __ldg(sv.table + (size_t)ri * sv.K + di);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (slot[u] >= 0) v[slot[u]] = t[u];
+        }
+        named_bar_arrive(1 + (use & 1), RL_OVERLAP_THREADS);  // FULL[b]
+      }
+    }
+  } else {
+    const int lane = threadIdx.x & 31;
+    for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+      const int p0 = g * ppb;
+      const int np = min(ppb, N - p0);
+      double w = 1.0;
+      for (int c0 = 0; c0 < M; c0 += chunk, ++use) {
+        const int cm = min(chunk, M - c0);
+        const double* v = vals + (use & 1) * buf_elems + lane * stride;
+        named_bar_sync(1 + (use & 1), RL_OVERLAP_THREADS);  // FULL[b]
+        if (lane < np)
+          for (int a = 0; a < cm; ++a) w = __dmul_rn(w, v[a]);  // reference order: beam ascending
+        named_bar_arrive(3 + (use & 1), RL_OVERLAP_THREADS);  // FREE[b]
+      }
+      if (lane < np) {
+        const size_t i = perm ? (size_t)__ldg(perm + p0 + lane) : (size_t)(out_base + p0 + lane);
+        if (peers.n == 0) {
+          weights[i] = w;
+        } else {
+          for (int r = 0; r < peers.n; ++r) out_ptrs[r][peers.offset + i] = w;
+        }
+      }
+    }
+  }
+  if (peers.sig && sig_last) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned done = atomicAdd(peers.counter, 1u);
+      if (done == gridDim.x - 1) {
+        *peers.counter = 0u;
+        __threadfence_system();
+        *(volatile long long*)peers.epoch = epoch;
+        for (int r = 0; r < peers.n; ++r) ((volatile long long*)peers.flags[r])[peers.rank] = epoch;
+      }
+    }
+  }
+}
+
 // consumer-side wait of the signalled mode: returns (on the stream) once every rank's slice of the
 // latest epoch launched on this rank has arrived
 __global__ void peers_wait_kernel(PeerOut peers) {
@@ -1760,6 +1885,72 @@ static int block_burst_pairs() {  // tuning knob of rm_march_block (RL_BLOCK_BUR
   return v;
 }
 
+// eval_overlap_kernel over n particles whose ranges start at `ranges`; weight of particle i goes to perm[i] if perm,
+// else to out_base + i
+static int launch_eval_overlap(rl_method* m, float range_scale, const float* obs, const float* ranges, double* weights,
+                               int n, int M, long long out_base, const int* perm, const PeerOut& po, bool sig_first,
+                               bool sig_last) {
+  const int pieces = (M + 63) / 64;
+  const int chunk = max(1, (M + pieces - 1) / pieces);  // <= 64 beams at a time, pieces of equal length
+  const int ppb = 32;
+  const size_t smem = 2 * (size_t)ppb * (chunk | 1) * sizeof(double);
+  const int groups = (n + ppb - 1) / ppb;
+  const int grid = max(1, min(groups, sm_count() * resident_ctas(eval_overlap_kernel, RL_OVERLAP_THREADS, 6, smem)));
+  eval_overlap_kernel<<<grid, RL_OVERLAP_THREADS, smem, m->stream>>>(m->sensor_view(), m->xf.inv_scale, range_scale, obs,
+                                                                    ranges, weights, n, M, ppb, chunk, out_base, perm, po,
+                                                                    sig_first ? 1 : 0, sig_last ? 1 : 0);
+  count_launch();
+  RL_CHECK_LAUNCH();
+  return RL_OK;
+}
+
+template <int KIND>
+static int launch_cast_kind(rl_method* m, int mode, const float* ins, const float* angles, const float* obs,
+                            float* outs, double* weights, int n, int M, const PeerOut* peers);
+
+// A deep fused update as cast-to-memory + evaluation, in chunks of particles whose ranges fit the scratch array
+// (RL_TWOSTEP_SCRATCH_MB, default 1024).  perm (tile order, or null) is the processing order of the whole cloud.
+template <int KIND>
+static int launch_fused_twostep(rl_method* m, const float* ins, const float* angles, const float* obs, double* weights,
+                                int n, int M, const PeerOut& po, const int* perm) {
+  static const size_t scratch_mb = getenv("RL_TWOSTEP_SCRATCH_MB") ? (size_t)max(16, atoi(getenv("RL_TWOSTEP_SCRATCH_MB"))) : 1024;
+  const size_t per_particle = (size_t)M * sizeof(float);
+  int cap = (int)max((size_t)1024, min((size_t)n, (scratch_mb << 20) / per_particle));
+  const int nchunks = (n + cap - 1) / cap;
+  cap = (n + nchunks - 1) / nchunks;  // chunks of equal size
+  const size_t want = (size_t)cap * per_particle;
+  if (want > m->ts_ranges_bytes) {
+    cudaFree(m->d_ts_ranges);
+    m->d_ts_ranges = nullptr;
+    m->ts_ranges_bytes = 0;
+    RL_CUDA(cudaMalloc(&m->d_ts_ranges, want));
+    m->ts_ranges_bytes = want;
+  }
+  if (perm && (size_t)cap * 12 > m->ts_poses_bytes) {
+    cudaFree(m->d_ts_poses);
+    m->d_ts_poses = nullptr;
+    m->ts_poses_bytes = 0;
+    RL_CUDA(cudaMalloc(&m->d_ts_poses, (size_t)cap * 12));
+    m->ts_poses_bytes = (size_t)cap * 12;
+  }
+  for (int c0 = 0; c0 < n; c0 += cap) {
+    const int np = min(cap, n - c0);
+    const float* poses = ins + 3 * (size_t)c0;
+    if (perm) {
+      gather_poses_kernel<<<(np + 255) / 256, 256, 0, m->stream>>>(ins, perm + c0, m->d_ts_poses, np);
+      count_launch();
+      RL_CHECK_LAUNCH();
+      poses = m->d_ts_poses;
+    }
+    const int rc = launch_cast_kind<KIND>(m, MODE_ANGLES, poses, angles, nullptr, m->d_ts_ranges, nullptr, np, M, nullptr);
+    if (rc) return rc;
+    const int rc2 = launch_eval_overlap(m, 1.0f, obs, m->d_ts_ranges, weights, np, M, c0, perm ? perm + c0 : nullptr, po,
+                                        c0 == 0, c0 + cap >= n);
+    if (rc2) return rc2;
+  }
+  return RL_OK;
+}
+
 template <int KIND>
 static int launch_cast_kind(rl_method* m, int mode, const float* ins, const float* angles, const float* obs,
                             float* outs, double* weights, int n, int M, const PeerOut* peers) {
@@ -1812,6 +2003,18 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
       const int rc = spatial_order(m, ins, n, &perm);
       if (rc) return rc;
     }
+    // deep updates: cast to memory + evaluation (see eval_overlap_kernel).  RL_FUSED_TWOSTEP=0 keeps the fused kernels.
+    static const int twostep_env = getenv("RL_FUSED_TWOSTEP") ? atoi(getenv("RL_FUSED_TWOSTEP")) : -1;
+    // Measured per kind (B200, G rays/s, fused kernels -> two kernels; profiles/r02/twostep_r02.log): RM on the 8192^2
+    // map 200000 x 1080 25.9 -> 35.9; RM on the 5 cm map 20000 x 1080 37.7 -> 38.6, 50000 x 360 33.5 -> 33.9, 100000 x 60
+    // 26.7 -> 25.8 (the re-queuing fused kernel keeps short fans on structures that fit L2); CDDT 100000 x 60 37.4 ->
+    // 43.0, 50000 x 360 51.3 -> 62.3, 20000 x 1080 58.5 -> 75.3; GiantLUT 42.8 -> 44.3 / 42.6 -> 65.4 / 58.4 -> 94.4;
+    // BL 2000 x 1080 2.42 -> 2.79.  RL_FUSED_TWOSTEP = bit mask of kinds (1 << kind) overrides.
+    const bool twostep_kind = twostep_env >= 0 ? (twostep_env & (1 << KIND)) != 0
+                                               : (KIND != RL_RM || M > 128 || struct_bytes > ((size_t)48 << 20));
+    if (twostep_kind && mv.coop_threshold == 0 && m->persist && m->max_range > 0.0f &&
+        (long long)n * M >= (long long)sm_count() * 48 * 64 * 4)
+      return launch_fused_twostep<KIND>(m, ins, angles, obs, weights, n, M, po, perm);
     static const bool deep = !(getenv("RL_FUSED_PERSIST") && atoi(getenv("RL_FUSED_PERSIST")) == 0);
     static const int group_rays = getenv("RL_FUSED_GROUP_RAYS") ? atoi(getenv("RL_FUSED_GROUP_RAYS")) : RL_FUSED_GROUP_RAYS;
     // many waves deep and at least six particles per group: the re-queuing kernel (measured, basement 5 cm map:
@@ -2018,6 +2221,9 @@ int launch_eval_sensor(rl_method* m, const float* obs, const float* ranges, doub
     set_error("eval_sensor_model: set_sensor_model has not been called");
     return RL_E_STATE;
   }
+  static const bool overlap = !(getenv("RL_EVAL_OVERLAP") && atoi(getenv("RL_EVAL_OVERLAP")) == 0);
+  if (overlap && n >= 64 * sm_count())  // at least two groups of 32 particles per SM: the streaming form
+    return launch_eval_overlap(m, m->xf.inv_scale, obs, ranges, outs, n, M, 0, nullptr, PeerOut{}, false, false);
   const int threads = 256;
   const int chunk = max(1, min(M, 2048));
   const int ppb = max(1, min(threads / max(M, 1), 32));

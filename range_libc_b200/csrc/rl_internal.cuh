@@ -208,6 +208,12 @@ struct rl_method {
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   int sort_cap = 0;
+  // deep fused updates as cast + eval (rl_cast.cu, launch_fused_twostep): ranges of one chunk of particles, and the
+  // chunk's poses in processing order when the cloud is tile-ordered
+  float* d_ts_ranges = nullptr;
+  size_t ts_ranges_bytes = 0;
+  float* d_ts_poses = nullptr;
+  size_t ts_poses_bytes = 0;
   // particle-filter steps (rl_pf.cu): reduction result, fixed-point weights / prefix sums, cub scratch
   void* d_pf = nullptr;
   size_t pf_bytes = 0;
