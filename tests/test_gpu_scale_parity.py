@@ -186,7 +186,7 @@ def test_c5_million_particles_1080_beams_8192():
     assert hashlib.sha256(got.tobytes()).hexdigest() == hashlib.sha256(w2.cpu().numpy().tobytes()).hexdigest()
 
 
-@pytest.mark.parametrize("kn,n,m_beams", [("rm", 2600, 1080), ("cddt", 12002, 60), ("pcddt", 9001, 97), ("rm", 3000, 700)])
+@pytest.mark.parametrize("kn,n,m_beams", [("rm", 2600, 1080), ("cddt", 12002, 60), ("pcddt", 9001, 97), ("rm", 2500, 700)])
 def test_deep_fused_updates_with_the_product_warp(kn, n, m_beams):
     """Deep fused launches on a structure that fits L2 run fused_overlap_kernel (a ninth warp forms the products while
     the others march the next group; named barriers, two value buffers): at least two groups per resident CTA, odd
