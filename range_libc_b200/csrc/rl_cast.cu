@@ -1942,7 +1942,12 @@ static int launch_fused_twostep(rl_method* m, const float* ins, const float* ang
       RL_CHECK_LAUNCH();
       poses = m->d_ts_poses;
     }
+    // the fused update indexes the table with the range in PIXELS (RangeLib.h:602-603): the cast must not apply the
+    // world scale that numpy_calc_range_angles applies to its outputs (x 1.0f is exact)
+    const float world_scale = m->xf.scale;
+    m->xf.scale = 1.0f;
     const int rc = launch_cast_kind<KIND>(m, MODE_ANGLES, poses, angles, nullptr, m->d_ts_ranges, nullptr, np, M, nullptr);
+    m->xf.scale = world_scale;
     if (rc) return rc;
     const int rc2 = launch_eval_overlap(m, 1.0f, obs, m->d_ts_ranges, weights, np, M, c0, perm ? perm + c0 : nullptr, po,
                                         c0 == 0, c0 + cap >= n);

@@ -218,6 +218,48 @@ def test_deep_fused_updates_with_the_product_warp(kn, n, m_beams):
     assert np.isfinite(w.cpu().numpy()[7])
 
 
+@pytest.mark.parametrize("kn,n,m_beams", [("rm", 2400, 1080), ("rm", 40000, 60), ("cddt", 36000, 60), ("cddt", 9000, 60),
+                                          ("bl", 2100, 1080)])
+def test_deep_fused_updates_under_world_parameters(kn, n, m_beams):
+    """Deep fused updates with a 5 cm world scale, an origin and a map rotation, through every deep route (cast to memory +
+    evaluation, the re-queuing fused kernel, the product-warp kernel): the table is indexed with the range in pixels and
+    the observation scaled by 1 / world scale (RangeLib.h:596-606), whatever numpy_calc_range_angles does to its own
+    outputs.  Weights bit-equal to the oracle."""
+    import torch
+    occ = wl.load_map("basement_hallways_10cm")
+    ang = 0.3
+    world = (0.05, ang, -12.5, 7.25, float(np.sin(ang)), float(np.cos(ang)))
+    om = omap_of(occ)
+    om.set_world(*world)
+    meth = method(kn, om)
+    table = wl.sensor_table(501)
+    meth.set_sensor_model(table)
+    W, H = occ.shape
+    grid = wl.random_queries(W, H, n, seed=33)
+    parts = wl.grid_to_world(grid, world[0], world[2], world[3], world[1])
+    angles = wl.lidar_angles(m_beams)
+    obs = (np.clip(60 + 50 * np.sin(np.linspace(0, 6, m_beams)), 0, 500) * world[0]).astype(np.float32)
+    pd, ad, od = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (parts, angles, obs))
+    w = torch.full((n,), -1.0, dtype=torch.float64, device="cuda")
+    meth.calc_range_repeat_angles_eval_sensor_model(pd, ad, od, w)
+    meth.synchronize()
+    kind = {"rm": port.RM, "cddt": port.CDDT, "bl": port.BL}[kn]
+    ora = port.Oracle(kind, occ, MR, TD, threads=NTHREADS)
+    ora.set_world(*world)
+    ora.set_sensor_model(table)
+    want = ora.calc_range_repeat_angles_eval_sensor_model(parts, angles, obs)
+    assert_bit_equal(w.cpu().numpy(), want, "%s deep fused %d x %d under world parameters vs oracle" % (kn, n, m_beams))
+    # and the two-call form of the same update: ranges in world units, then eval_sensor_model
+    r = torch.empty(n * m_beams, dtype=torch.float32, device="cuda")
+    w2 = torch.empty(n, dtype=torch.float64, device="cuda")
+    meth.calc_range_repeat_angles(pd, ad, r)
+    meth.eval_sensor_model(od, r, w2, m_beams, n)
+    meth.synchronize()
+    want_r = ora.numpy_calc_range_angles(parts, angles)
+    assert_bit_equal(r.cpu().numpy(), want_r, "%s ranges under world parameters" % kn)
+    assert_bit_equal(w2.cpu().numpy(), ora.eval_sensor_model(obs, want_r, m_beams, n), "%s eval_sensor_model (streaming form)" % kn)
+
+
 def test_multi_gpu_torchrun_all_gather_paths():
     """All gather paths (NCCL, peer stores, signalled, pipelined, host-pointer sharded call through both bindings)
     bit-equal to the oracle on every rank; needs two visible GPUs."""
