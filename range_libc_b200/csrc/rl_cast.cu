@@ -1263,7 +1263,9 @@ fused_overlap_kernel(MapView mv, CddtView cv, WorldXform xf, SensorView sv, floa
 // rays that end with the slowest ray of the round, a barrier, the product), while the ranges cost 8 bytes of HBM
 // traffic per ray there and back, 5 % of the bandwidth at that rate.  Fusing is a latency device for launches that fit
 // the chip once; a deep update is the persistent lane-re-queuing cast into a scratch array followed by a streaming
-// evaluation (launch_fused_twostep).
+// evaluation (launch_fused_twostep).  Measured and dropped: the table lookup in the cast's epilogue, the second kernel
+// only multiplying 8-byte values -- 35.9 -> 33.1 G rays/s on the 8192^2 map, 38.6 -> 36.2 on the 5 cm map: the gather and
+// its index arithmetic cost the issue-bound cast more than the streaming kernel pays for them.
 // eval_overlap_kernel: the sensor-model half (RangeLib.h:533-555 / :596-610) in fused_overlap_kernel's form -- eight
 // loader warps turn ranges into table values (coalesced range loads four deep, one table gather each) for a group of up
 // to 32 particles and a chunk of beams, the ninth warp multiplies, lane p = particle p, beam order, running product
