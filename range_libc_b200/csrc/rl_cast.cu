@@ -1281,7 +1281,10 @@ __global__ void gather_poses_kernel(const float* __restrict__ ins, const int* __
   out[3 * (size_t)i + 2] = __ldg(ins + 3 * s + 2);
 }
 
-__global__ void __launch_bounds__(RL_OVERLAP_THREADS, 7)
+#ifndef RL_EVAL_MINB
+#define RL_EVAL_MINB 4
+#endif
+__global__ void __launch_bounds__(RL_OVERLAP_THREADS, RL_EVAL_MINB)
 eval_overlap_kernel(SensorView sv, float obs_scale, float range_scale, const float* __restrict__ obs,
                     const float* __restrict__ ranges, double* __restrict__ weights, int N, int M, int ppb, int chunk,
                     long long out_base, const int* __restrict__ perm, PeerOut peers, int sig_first, int sig_last) {
@@ -1305,42 +1308,39 @@ eval_overlap_kernel(SensorView sv, float obs_scale, float range_scale, const flo
   double* const* out_ptrs = (peers.sig && (epoch & 1)) ? peers.ptr1 : peers.ptr;
   int use = 0;
   if (threadIdx.x < RL_OVERLAP_MARCHERS) {
+    // Loader warp w takes particles w, w + 8, w + 16, w + 24 of the group (ppb <= 32); its lanes take beams lane and
+    // lane + 32 of the chunk (chunk <= 64).  The observation's table row is therefore fixed per lane and chunk: one
+    // row pointer per half, no index division, and every range load is a 128-byte row segment.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int g = blockIdx.x; g < groups; g += gridDim.x) {
       const int p0 = g * ppb;
       const int np = min(ppb, N - p0);
       for (int c0 = 0; c0 < M; c0 += chunk, ++use) {
         const int cm = min(chunk, M - c0);
-        const int rays = np * cm;
-        const float rcp_cm = rcp_floor((unsigned)cm);
+        const bool h0 = lane < cm, h1 = lane + 32 < cm;
+        const double* __restrict__ row0 =
+            sv.table + (size_t)sensor_index(fmul(__ldg(obs + c0 + (h0 ? lane : 0)), obs_scale), kmax) * sv.K;
+        const double* __restrict__ row1 =
+            sv.table + (size_t)sensor_index(fmul(__ldg(obs + c0 + (h1 ? lane + 32 : 0)), obs_scale), kmax) * sv.K;
         double* v = vals + (use & 1) * buf_elems;
+        float r[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int p = warp + 8 * q;
+          const float* __restrict__ base = ranges + (size_t)(p0 + min(p, np - 1)) * M + c0;
+          r[2 * q] = h0 ? __ldg(base + lane) : 0.0f;
+          r[2 * q + 1] = h1 ? __ldg(base + lane + 32) : 0.0f;
+        }
         if (use >= 2) named_bar_sync(3 + (use & 1), RL_OVERLAP_THREADS);  // FREE[b]
-        for (int k0 = threadIdx.x; k0 < rays; k0 += 4 * RL_OVERLAP_MARCHERS) {
-          float r[4];
-          int slot[4], a[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int k = k0 + u * RL_OVERLAP_MARCHERS;
-            slot[u] = -1;
-            a[u] = c0;
-            r[u] = 0.0f;
-            if (k < rays) {
-              unsigned up, uj;
-              divmod_small((unsigned)k, (unsigned)cm, rcp_cm, &up, &uj);  // k < ppb * cm <= 65536
-              a[u] = c0 + (int)uj;
-              slot[u] = (int)up * stride + (int)uj;
-              r[u] = __ldg(ranges + (size_t)(p0 + (int)up) * M + a[u]);
-            }
+        for (int q = 0; q < 4; ++q) {
+          const int p = warp + 8 * q;
+          const double t0 = __ldg(row0 + sensor_index(fmul(r[2 * q], range_scale), kmax));
+          const double t1 = __ldg(row1 + sensor_index(fmul(r[2 * q + 1], range_scale), kmax));
+          if (p < np) {
+            if (h0) v[p * stride + lane] = t0;
+            if (h1) v[p * stride + lane + 32] = t1;
           }
-          double t[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int di = sensor_index(fmul(r[u], range_scale), kmax);
-            const int ri = sensor_index(fmul(__ldg(obs + a[u]), obs_scale), kmax);
-            t[u] = __ldg(sv.table + (size_t)ri * sv.K + di);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (slot[u] >= 0) v[slot[u]] = t[u];
         }
         named_bar_arrive(1 + (use & 1), RL_OVERLAP_THREADS);  // FULL[b]
       }
