@@ -14,8 +14,9 @@ Workloads (--workload auto picks by the number of GPUs):
                fractions and a CPU baseline timed in the same run.
   c5  (N > 1)  BASELINE configs[4]: 1 000 000 particles x 1080 beams on a synthetic 8192^2 grid, STRONG scaling: the
                particles are sharded over the ranks (one process per GPU, map / distance transform / table replicated),
-               every step ends with all ranks holding all weights (the fused kernel's epilogue stores each weight
-               into every rank's gathered array over NVLink and signals completion; no cross-step pipelining).
+               every step ends with all ranks holding all weights (a deep update is a lane-re-queuing cast into a
+               scratch array followed by the evaluation kernel, whose epilogue stores each weight into every rank's
+               gathered array over NVLink and signals completion; no NCCL call, no cross-step pipelining).
                Rank 0 also times the same update on its GPU alone (`strong_scaling_base`), and every rank checks the
                gathered weights against a single-GPU recomputation of all shards (`gather_verified`).
 `--impl reference` times the reference's own CPU implementation (oracle/_ref, unmodified RangeLib.h) on the same
@@ -60,6 +61,20 @@ def workload_config(name):
             "l2": "GPU arm: the 268 MB distance transform exceeds the 126 MB L2 (inputs larger than L2); the 12 MB of poses are "
                   "device resident for `value` and cross PCIe every step for `e2e`",
             "parallelism": "particles sharded over the ranks in contiguous slices, map / distance transform / table replicated"}
+
+
+def profiled_update(name, kernel_substrs):
+    """DRAM bytes / L2 sector bytes / seconds of one UPDATE made of several kernels: the per-kernel means of a committed
+    warm capture (profiled), summed.  None when any of them is absent."""
+    parts = [profiled(name, k) for k in kernel_substrs]
+    if any(p is None for p in parts):
+        return None
+    return {"dram_bytes": sum(p["dram_bytes"] for p in parts), "l2_sector_bytes": sum(p["l2_sector_bytes"] for p in parts),
+            "seconds": sum(p["seconds"] for p in parts), "launches": sum(p["launches"] for p in parts),
+            "per_kernel_seconds": {k: p["seconds"] for k, p in zip(kernel_substrs, parts)}, "source": parts[0]["source"]}
+
+
+C5_KERNELS = ("rm_persist_kernel", "eval_overlap_kernel")  # the two kernels of a deep fused RM update
 
 
 def load_peaks():
@@ -573,9 +588,9 @@ def run_c5(args, rank, local_rank, world):
     upd = None
     if world > 1:
         upd = parallel.SignalledSensorUpdate(C5_PART, rm, angles, obs, device=dev)
-        gather_mode = ("one kernel per rank and step: fused compute + peer stores of every weight into each rank's gathered "
-                       "array over NVLink (symmetric memory, double buffered) + in-kernel epoch flags, then a wait kernel; "
-                       "no NCCL call, no cross-step pipelining")
+        gather_mode = ("per rank and step: tile sort of the shard, fan cast into a scratch array, evaluation kernel whose "
+                       "epilogue stores every weight into each rank's gathered array over NVLink (symmetric memory, double "
+                       "buffered) and raises in-kernel epoch flags, then a wait kernel; no NCCL call, no cross-step pipelining")
         w_local = None
     else:
         w_local = torch.empty(C5_PART, dtype=torch.float64, device=dev)
@@ -632,7 +647,7 @@ def run_c5(args, rank, local_rank, world):
     if world > 1:
         host_upd = parallel.HostShardedSensorUpdate(C5_PART, m_e2e, device=dev)
         e2e_api = ("%s.PyRayMarchingGPU.calc_range_repeat_angles_eval_sensor_model_sharded(numpy host arrays): H2D of this "
-                   "rank's particles, signalled fused kernel with peer stores, wait, D2H of all weights"
+                   "rank's particles, cast + signalled evaluation kernel with peer stores, wait, D2H of all weights"
                    % ("range_libc [Cython drop-in]" if cy is not None else "range_libc_b200"))
 
         def e2e_step():
@@ -694,16 +709,21 @@ def run_c5(args, rank, local_rank, world):
     if rank == 0:
         peak, peak_src = load_peaks()
         n_local = hi - lo
-        prof = profiled("c5", "fused_kernel")
+        prof = profiled_update("c5_twostep", C5_KERNELS)
         # compulsory bytes of the fused call (12 N + 8 M in, 8 N out -- out once per peer when sharded)
         algo_bytes = 12 * n_local + 8 * C5_BEAMS + 8 * n_local * max(world, 1)
         kernel_s = ms * 1e-3 / K_
         achieved = algo_bytes / kernel_s / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "fused_kernel<RM> (M = 1080: one particle per CTA iteration)",
+                "traffic": None,
+                "kernel": "rm_persist_kernel<ANGLES> (lane-re-queuing fan cast into a scratch array, ~90 % of the update) + "
+                          "eval_overlap_kernel (table lookups + ordered products)",
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
-                "note": "compulsory-only figure (0.0185 B/ray): the fused update is bound by instruction issue and L2 "
-                        "gathers, not by HBM"}
+                "note": "compulsory-only figure (0.0185 B/ray): a deep fused update runs as two kernels, the cast is bound "
+                        "by instruction issue (issue slots 79 % busy, profiles/r02/ncu_c5_twostep.txt), not by HBM; the "
+                        "ranges between the two kernels are the 8 B/ray of structure traffic counted in `traffic`"}
+        if prof:
+            roof["kernel_share_of_update"] = {k: v / prof["seconds"] for k, v in prof["per_kernel_seconds"].items()}
         if prof:
             # the capture is a 200 000-particle launch of the same kernel on the same map: scale per particle
             per_particle = prof["dram_bytes"] / 200000.0
@@ -711,9 +731,10 @@ def run_c5(args, rank, local_rank, world):
             roof["traffic_source"] = prof["source"] + ", 200 000-particle launch scaled to this rank's shard"
             roof["with_structure_traffic"] = {"achieved": per_particle * n_local / kernel_s / 1e9,
                                               "frac": per_particle * n_local / kernel_s / 1e9 / peak,
-                                              "what": "measured DRAM bytes (distance-transform sectors that miss L2 + poses + "
-                                                      "weights) over the kernel time: tile-ordered processing keeps the 268 MB "
-                                                      "distance transform's working set in L2 (hit rate 97 %)"}
+                                              "what": "measured DRAM bytes of both kernels (distance-transform sectors that miss "
+                                                      "L2 + ranges written and read back + poses + weights) over the update time: "
+                                                      "tile-ordered processing keeps the 268 MB distance transform's working set in "
+                                                      "L2 (hit rate 91 %)"}
         cfg = workload_config("c5")
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": K_, "warmup": W_,
@@ -945,7 +966,7 @@ def extra_throughput(rl, wl, occ, omap, dev, stream, peak, threads):
         w5 = torch.empty(C5_PART, dtype=torch.float64, device=dev)
         t = _time_launches(lambda: rm5.calc_range_repeat_angles_eval_sensor_model(p5, a5, o5, w5), stream, iters=3, warm=1)
         rate = C5_PART * C5_BEAMS / t
-        prof = profiled("c5", "fused_kernel")
+        prof = profiled_update("c5_twostep", C5_KERNELS)
         sets = [np.ascontiguousarray(p5_h[i * 10000:(i + 1) * 10000]) for i in range(4)]
         v, kind, done, dtc = cpu_fused_run(occ5, sets, a5_h, o5_h, table, 8, 0, threads, budget_s=6.0)
         out["c5_rm_fused_8192"] = {"particles": C5_PART, "beams": C5_BEAMS, "s_per_update": t, "rays_per_s": rate,
@@ -955,7 +976,8 @@ def extra_throughput(rl, wl, occ, omap, dev, stream, peak, threads):
                                    "cpu": {"rays_per_s": v, "kind": kind, "threads": threads,
                                            "sample": "%d steps of 10 000 particles x 1080 beams" % done},
                                    "note": "268 MB distance transform (> L2); big clouds are processed in tile order so its working "
-                                           "set stays in L2"}
+                                           "set stays in L2; a deep update runs as two kernels (lane-re-queuing cast into a scratch "
+                                           "array in chunks of <= 1 GB of ranges, then the streaming evaluation)"}
         del rm5, p5, w5, m5
     except Exception as ex:  # noqa: BLE001
         out["c5_error"] = str(ex)[:200]

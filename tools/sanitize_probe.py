@@ -127,3 +127,18 @@ for pruned in (False, True):
     c2.set_sensor_model(table)
     c2.calc_range_repeat_angles_eval_sensor_model(cdp, angles, obs, cw)
 print("fused_overlap paths ok", float(dw.mean()), float(cw.mean()))
+
+# deep update as two kernels (launch_fused_twostep): fan cast into the scratch array + eval_overlap_kernel, RM and CDDT,
+# and the streaming eval_sensor_model on a batch of >= 64 particles per SM
+tp = wl.pf_particles_uniform(occ, 2750, seed=15)
+tw = np.empty(len(tp), np.float64)
+rm2.calc_range_repeat_angles_eval_sensor_model(tp, ma, mo, tw)
+c3 = rl.PyCDDTCast(omap, 256.0, 24)
+c3.set_sensor_model(table)
+cp3 = wl.pf_particles_uniform(occ, 32000, seed=16)
+cw3 = np.empty(len(cp3), np.float64)
+c3.calc_range_repeat_angles_eval_sensor_model(cp3, angles, obs, cw3)
+er = np.random.default_rng(17).uniform(0, 250, 12000 * 60).astype(np.float32)
+ew = np.empty(12000, np.float64)
+rm2.eval_sensor_model(obs, er, ew, 60, 12000)
+print("two-kernel deep update paths ok", float(tw.mean()), float(cw3.mean()), float(ew.mean()))
