@@ -1910,31 +1910,45 @@ template <int KIND>
 static int launch_cast_kind(rl_method* m, int mode, const float* ins, const float* angles, const float* obs,
                             float* outs, double* weights, int n, int M, const PeerOut* peers);
 
-// A deep fused update as cast-to-memory + evaluation, in chunks of particles whose ranges fit the scratch array
-// (RL_TWOSTEP_SCRATCH_MB, default 1024).  perm (tile order, or null) is the processing order of the whole cloud.
-template <int KIND>
-static int launch_fused_twostep(rl_method* m, const float* ins, const float* angles, const float* obs, double* weights,
-                                int n, int M, const PeerOut& po, const int* perm) {
+// Scratch of a two-kernel deep update: ranges of one chunk of particles (RL_TWOSTEP_SCRATCH_MB, default 1024; a quarter
+// and a sixteenth of it are tried when the allocation fails) and, for tile-ordered clouds, the chunk's poses in
+// processing order.  Returns the particles per chunk, or 0 when there is no memory for it -- the caller then keeps the
+// fused kernels, which need none.  (Allocates on first use, like the handle's other scratch: capture a deep update into
+// a CUDA graph only after one warm-up call.)
+static int twostep_chunk(rl_method* m, int n, int M, bool ordered) {
   static const size_t scratch_mb = getenv("RL_TWOSTEP_SCRATCH_MB") ? (size_t)max(16, atoi(getenv("RL_TWOSTEP_SCRATCH_MB"))) : 1024;
   const size_t per_particle = (size_t)M * sizeof(float);
-  int cap = (int)max((size_t)1024, min((size_t)n, (scratch_mb << 20) / per_particle));
-  const int nchunks = (n + cap - 1) / cap;
-  cap = (n + nchunks - 1) / nchunks;  // chunks of equal size
-  const size_t want = (size_t)cap * per_particle;
-  if (want > m->ts_ranges_bytes) {
-    cudaFree(m->d_ts_ranges);
-    m->d_ts_ranges = nullptr;
-    m->ts_ranges_bytes = 0;
-    RL_CUDA(cudaMalloc(&m->d_ts_ranges, want));
-    m->ts_ranges_bytes = want;
+  for (size_t budget = scratch_mb << 20; budget >= ((size_t)16 << 20); budget >>= 2) {
+    int cap = (int)max((size_t)1024, min((size_t)n, budget / per_particle));
+    const int nchunks = (n + cap - 1) / cap;
+    cap = (n + nchunks - 1) / nchunks;  // chunks of equal size
+    const size_t want = (size_t)cap * per_particle;
+    bool ok = true;
+    if (want > m->ts_ranges_bytes) {
+      cudaFree(m->d_ts_ranges);
+      m->d_ts_ranges = nullptr;
+      m->ts_ranges_bytes = 0;
+      ok = cudaMalloc(&m->d_ts_ranges, want) == cudaSuccess;
+      if (ok) m->ts_ranges_bytes = want;
+    }
+    if (ok && ordered && (size_t)cap * 12 > m->ts_poses_bytes) {
+      cudaFree(m->d_ts_poses);
+      m->d_ts_poses = nullptr;
+      m->ts_poses_bytes = 0;
+      ok = cudaMalloc(&m->d_ts_poses, (size_t)cap * 12) == cudaSuccess;
+      if (ok) m->ts_poses_bytes = (size_t)cap * 12;
+    }
+    if (ok) return cap;
+    cudaGetLastError();  // out of memory: try a smaller chunk
   }
-  if (perm && (size_t)cap * 12 > m->ts_poses_bytes) {
-    cudaFree(m->d_ts_poses);
-    m->d_ts_poses = nullptr;
-    m->ts_poses_bytes = 0;
-    RL_CUDA(cudaMalloc(&m->d_ts_poses, (size_t)cap * 12));
-    m->ts_poses_bytes = (size_t)cap * 12;
-  }
+  return 0;
+}
+
+// A deep fused update as cast-to-memory + evaluation, in chunks of `cap` particles (twostep_chunk).  perm (tile order,
+// or null) is the processing order of the whole cloud.
+template <int KIND>
+static int launch_fused_twostep(rl_method* m, const float* ins, const float* angles, const float* obs, double* weights,
+                                int n, int M, const PeerOut& po, const int* perm, int cap) {
   for (int c0 = 0; c0 < n; c0 += cap) {
     const int np = min(cap, n - c0);
     const float* poses = ins + 3 * (size_t)c0;
@@ -2020,8 +2034,10 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
     const bool twostep_kind = twostep_env >= 0 ? (twostep_env & (1 << KIND)) != 0
                                                : (KIND != RL_RM || M > 128 || struct_bytes > ((size_t)48 << 20));
     if (twostep_kind && mv.coop_threshold == 0 && m->persist && m->max_range > 0.0f &&
-        (long long)n * M >= (long long)sm_count() * 48 * 64 * 4)
-      return launch_fused_twostep<KIND>(m, ins, angles, obs, weights, n, M, po, perm);
+        (long long)n * M >= (long long)sm_count() * 48 * 64 * 4) {
+      const int cap = twostep_chunk(m, n, M, perm != nullptr);
+      if (cap > 0) return launch_fused_twostep<KIND>(m, ins, angles, obs, weights, n, M, po, perm, cap);
+    }
     static const bool deep = !(getenv("RL_FUSED_PERSIST") && atoi(getenv("RL_FUSED_PERSIST")) == 0);
     static const int group_rays = getenv("RL_FUSED_GROUP_RAYS") ? atoi(getenv("RL_FUSED_GROUP_RAYS")) : RL_FUSED_GROUP_RAYS;
     // many waves deep and at least six particles per group: the re-queuing kernel (measured, basement 5 cm map:
