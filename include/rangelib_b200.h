@@ -186,7 +186,7 @@ int rl_method_peers_wait(rl_method* m);
 /* The sharded particle-filter update as ONE blocking call with HOST buffers (what a multi-process particle filter
  * written against the reference's calc_range_repeat_angles_eval_sensor_model would call on each rank; replaces the
  * loop RangeLib.h:558-612 over ALL particles): this rank's `num_particles` poses (the slice starting at particle
- * `offset` of `n_total`) are copied to the device, the signalled fused kernel computes their weights and stores them
+ * `offset` of `n_total`) are copied to the device, the signalled update (one fused kernel, or cast + evaluation kernel for deep updates) computes their weights and stores them
  * into every rank's gathered array over NVLink, and after every rank's slice has arrived the whole gathered array
  * (n_total doubles) is copied into weights_all.  Needs rl_method_peers_init; every rank must call it the same number
  * of times.  With DEVICE pointers nothing blocks: the copy into weights_all is device-to-device on the handle's stream. */

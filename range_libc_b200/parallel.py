@@ -3,7 +3,7 @@ map / distance transform / sensor table replicated, per-particle weights gathere
 (SURVEY.md section 8e).  Plain ray batches need no collective; only the weights are exchanged.
 
 Gather paths:
-  * "peer":      the fused kernel's epilogue stores each weight straight into every rank's gathered
+  * "peer":      the epilogue of the kernel that forms the weights stores each one straight into every rank's gathered
                  array over NVLink (rl_calc_range_repeat_angles_eval_sensor_model_peers); the arrays
                  live in torch symmetric memory, and a symmetric-memory barrier orders the step.
   * "signalled": the same stores plus in-kernel epoch flags: one kernel per rank and step, no barrier launch.
