@@ -243,9 +243,31 @@ class Marshal {
 // Also measured and dropped: CTAs fetching their poses from mapped host memory instead of the copy (56 us: a
 // thousand 48-byte PCIe reads), and a completion flag in host memory raised by the last CTA after a system-scope
 // fence instead of the stream synchronisation (+2 us).
+#ifdef RL_HOST_TIMING
+#include <time.h>
+static double g_ht[8];
+static long g_ht_n;
+static inline double ht_now() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+#define RL_HT(i) do { const double t_ = ht_now(); g_ht[i] += t_ - ht_prev; ht_prev = t_; } while (0)
+extern "C" void rl_debug_host_timing(double* out, long* n) {
+  for (int i = 0; i < 8; ++i) { out[i] = g_ht[i]; g_ht[i] = 0; }
+  *n = g_ht_n;
+  g_ht_n = 0;
+}
+#else
+#define RL_HT(i)
+#endif
 static int run_fused_host_small(rl_method* m, const float* ins, const float* angles, const float* obs, double* weights,
                                 int n, int M, bool* handled) {
   static const bool enabled = !(getenv("RL_HOST_DIRECT") && atoi(getenv("RL_HOST_DIRECT")) == 0);
+#ifdef RL_HOST_TIMING
+  double ht_prev = ht_now();
+  ++g_ht_n;
+#endif
   *handled = false;
   const size_t in_bytes = sizeof(float) * 3 * (size_t)n, out_bytes = sizeof(double) * (size_t)n;
   if (!enabled || M > RL_PARAM_BEAMS || in_bytes + out_bytes > Marshal::kSmallLimit) return RL_OK;
@@ -254,6 +276,7 @@ static int run_fused_host_small(rl_method* m, const float* ins, const float* ang
   if (s_ins == SIDE_DEVICE || s_w == SIDE_DEVICE || pointer_side(angles, &alias) == SIDE_DEVICE ||
       pointer_side(obs, &alias) == SIDE_DEVICE)
     return RL_OK;  // device or mixed pointers: the general path decides
+  RL_HT(0);  // pointer queries
   *handled = true;
   int rc = ensure_stage(m, in_bytes);
   if (!rc) rc = ensure_host_stage(m, align256(in_bytes) + out_bytes);
@@ -263,15 +286,20 @@ static int run_fused_host_small(rl_method* m, const float* ins, const float* ang
     memcpy(m->h_stage, ins, in_bytes);
     src = m->h_stage;
   }
+  RL_HT(1);  // staging
   RL_CUDA(cudaMemcpyAsync(m->d_stage, src, in_bytes, cudaMemcpyHostToDevice, m->stream));
+  RL_HT(2);  // H2D enqueue
   BeamParams beams;
   memcpy(beams.angles, angles, sizeof(float) * (size_t)M);
   memcpy(beams.obs, obs, sizeof(float) * (size_t)M);
   double* w_alias = (s_w == SIDE_PINNED) ? (double*)d_w : (double*)((char*)m->h_stage_dev + align256(in_bytes));
   rc = launch_fused_beam_params(m, (const float*)m->d_stage, beams, w_alias, n, M);
   if (rc) return rc;
+  RL_HT(3);  // kernel launch
   RL_CUDA(cudaStreamSynchronize(m->stream));
+  RL_HT(4);  // synchronise
   if (s_w != SIDE_PINNED) memcpy(weights, (char*)m->h_stage + align256(in_bytes), out_bytes);
+  RL_HT(5);  // copy out
   return RL_OK;
 }
 
