@@ -15,8 +15,16 @@
 //                             reference's order (beam 0..M-1) so weights are bit-identical;
 //                             multi-GPU epilogues (peer stores, epoch flags) live here too
 //   fused_rm_persist_kernel   the same call for RM clouds many waves deep: re-queuing inside particle groups
+//                             (short fans on structures within L2)
+//   fused_overlap_kernel<KIND> the same call, deep launches below ~1.8 M rays: the products on a ninth warp
+//                             behind named barriers, two value buffers
+//   launch_fused_twostep      the same call, deep launches from ~1.8 M rays on: the kind's big-batch cast
+//                             into a scratch array + eval_overlap_kernel (config 5 runs this way)
 //   radial_kernel<KIND>       RangeMethod::calc_range_many_radial_optimized :616-676 (CDDT calc_range_pair)
-//   eval_sensor_kernel        RangeMethod::eval_sensor_model              RangeLib.h:533-555
+//   eval_sensor_kernel        RangeMethod::eval_sensor_model              RangeLib.h:533-555 (small calls)
+//   eval_overlap_kernel       the same for big batches and as the second half of a deep fused update:
+//                             loader warps own particle rows (table row fixed per lane), a ninth warp
+//                             multiplies in beam order; multi-GPU epilogues as in fused_kernel
 //
 // KIND: RL_BL (:696-769), RL_RM (:927-962), RL_CDDT / RL_PCDDT (:1342-1516), RL_GLT (:1869-1880).
 #include <cstdlib>
