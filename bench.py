@@ -71,7 +71,9 @@ def profiled_update(name, kernel_substrs):
         return None
     return {"dram_bytes": sum(p["dram_bytes"] for p in parts), "l2_sector_bytes": sum(p["l2_sector_bytes"] for p in parts),
             "seconds": sum(p["seconds"] for p in parts), "launches": sum(p["launches"] for p in parts),
-            "per_kernel_seconds": {k: p["seconds"] for k, p in zip(kernel_substrs, parts)}, "source": parts[0]["source"]}
+            "per_kernel_seconds": {k: p["seconds"] for k, p in zip(kernel_substrs, parts)},
+            "per_kernel_issue_slots_busy": {k: p["issue_slots_busy"] for k, p in zip(kernel_substrs, parts)},
+            "source": parts[0]["source"]}
 
 
 C5_KERNELS = ("rm_persist_kernel", "eval_overlap_kernel")  # the two kernels of a deep fused RM update
@@ -107,12 +109,15 @@ def profiled(name, kernel_substr=None):
             cur["sectors"] = float(f[1].replace(",", ""))
         elif cur is not None and len(f) >= 3 and f[0] == "gpu__time_duration.sum":
             cur["seconds"] = float(f[1].replace(",", "")) * tscale.get(f[2], 1.0)
+        elif cur is not None and len(f) >= 2 and f[0] == "smsp__issue_active.avg.pct_of_peak_sustained_active":
+            cur["issue"] = float(f[1].replace(",", "")) / 100.0
     launches = [l for l in launches if kernel_substr is None or kernel_substr in l["kernel"]]
     if not launches:
         return None
     return {"dram_bytes": float(np.mean([l["dram"] for l in launches])),
             "l2_sector_bytes": float(np.mean([l.get("sectors", 0.0) for l in launches])) * 32.0,
             "seconds": float(np.mean([l.get("seconds", 0.0) for l in launches])), "launches": len(launches),
+            "issue_slots_busy": float(np.mean([l.get("issue", 0.0) for l in launches])),
             "source": "profiles/r02/ncu_%s.txt (ncu --set full --cache-control none, warm)" % name}
 
 
@@ -724,6 +729,9 @@ def run_c5(args, rank, local_rank, world):
                         "ranges between the two kernels are the 8 B/ray of structure traffic counted in `traffic`"}
         if prof:
             roof["kernel_share_of_update"] = {k: v / prof["seconds"] for k, v in prof["per_kernel_seconds"].items()}
+            roof["issue_slots_busy"] = dict(prof["per_kernel_issue_slots_busy"],
+                                            what="fraction of the SM issue slots in use (ncu smsp__issue_active, warm capture): "
+                                                 "the binding resource of the cast, which HBM is not")
         if prof:
             # the capture is a 200 000-particle launch of the same kernel on the same map: scale per particle
             per_particle = prof["dram_bytes"] / 200000.0
