@@ -1877,8 +1877,11 @@ static int fresh_work_cursor(rl_method* m, unsigned long long** out) {
 // rays a warp of a persistent kernel claims at a time: RL_CLAIM_RAYS (default 128; measured 128 / 256 / 512 / 1024 on
 // 2^24 random rays 38.5 / 38.9 / 38.3 / 34.8 G rays/s, BL 2^22 rays 2.46 / 2.28 / 2.42 / -), less when the batch is
 // small, so that every resident warp gets about four pieces
-static int claim_rays(long long total, long long resident_warps) {
-  static const int v = getenv("RL_CLAIM_RAYS") ? atoi(getenv("RL_CLAIM_RAYS")) : 128;
+// (lidar fans of >= 256 beams take 512 at a time -- half a particle's fan, neighbouring beams in one warp: 42.9 -> 43.6 G
+// rays/s on config 5's map, 200000 x 1080)
+static int claim_rays(long long total, long long resident_warps, int fan_beams = 0) {
+  static const int env = getenv("RL_CLAIM_RAYS") ? atoi(getenv("RL_CLAIM_RAYS")) : 0;
+  const int v = env > 0 ? env : (fan_beams >= 256 ? 512 : 128);
   static const int pieces = getenv("RL_CLAIM_PIECES") ? max(1, atoi(getenv("RL_CLAIM_PIECES"))) : 8;
   const long long even = (total / (resident_warps * pieces) + 31) / 32 * 32;
   return (int)max(32LL, min((long long)max(32, (v / 32) * 32), even));
@@ -2125,7 +2128,7 @@ static int launch_cast_kind(rl_method* m, int mode, const float* ins, const floa
                                      : resident_ctas(rm_persist_kernel<MODE_ANGLES, 1, false, true>, 256, RL_RM_PERSIST_MINB);
     const long long resident_warps = (long long)sm_count() * 8 * rm_ctas;
     if (KIND == RL_RM && m->max_range > 0.0f && total >= (long long)sm_count() * 48 * 64 && variant) {
-      const int chunk = claim_rays(total, resident_warps);
+      const int chunk = claim_rays(total, resident_warps, mode == MODE_ANGLES ? M : 0);
       const long long warps = min(resident_warps, (total + chunk - 1) / chunk);
       const int grid = (int)((warps + 7) / 8);
       unsigned long long* work = nullptr;
