@@ -11,6 +11,10 @@
 #include "rl_internal.cuh"
 #include "rl_math.cuh"
 
+#ifndef RL_SORT_TILE_SHIFT
+#define RL_SORT_TILE_SHIFT 6  // tiles of 64 x 64 cells
+#endif
+
 namespace rl {
 
 __device__ __forceinline__ unsigned spread_bits(unsigned v) {  // 0000abcd -> 0a0b0c0d (up to 16 bits)
@@ -36,7 +40,7 @@ __global__ void tile_key_kernel(WorldXform xf, const float* __restrict__ ins, in
   // first argument of calc_range (yy) runs along the map's x, the second (xx) along its y
   int cx = (yy >= 0.0f && yy < (float)W) ? __float2int_rz(yy) : 0;
   int cy = (xx >= 0.0f && xx < (float)H) ? __float2int_rz(xx) : 0;
-  keys[i] = spread_bits((unsigned)cx >> 6) | (spread_bits((unsigned)cy >> 6) << 1);
+  keys[i] = spread_bits((unsigned)cx >> RL_SORT_TILE_SHIFT) | (spread_bits((unsigned)cy >> RL_SORT_TILE_SHIFT) << 1);
   idx[i] = i;
 }
 
@@ -71,7 +75,9 @@ int spatial_order(rl_method* m, const float* d_ins, int n, const int** perm) {
   count_launch();
   RL_CHECK_LAUNCH();
   int bits = 2;
-  while (bits < 32 && (1u << (bits / 2)) < (unsigned)((max(m->W, m->H) + 63) >> 6)) bits += 2;
+  while (bits < 32 && (1u << (bits / 2)) <
+                          (unsigned)((max(m->W, m->H) + (1 << RL_SORT_TILE_SHIFT) - 1) >> RL_SORT_TILE_SHIFT))
+    bits += 2;
   cub::DoubleBuffer<unsigned> k(m->d_sort_keys, m->d_sort_keys + cap);
   cub::DoubleBuffer<int> v(m->d_sort_idx, m->d_sort_idx + cap);
   size_t tb = m->sort_tmp_bytes;
