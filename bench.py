@@ -439,10 +439,11 @@ def run_c2(args, local_rank):
     torch.cuda.synchronize()
     l0 = rl.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # K = 20 steps of ~23 us are over before the host has finished enqueueing them: a ~100 us spin kernel ahead of the
+    # K = 20 steps of ~23 us are over before the host has finished enqueueing them: a ~0.5 ms spin kernel ahead of the
     # first event keeps the stream busy while the events and the graph are enqueued, so the bracket holds the K steps
-    # and not the host's launch call (device time, as the timing rules ask; `timing` in the line says so)
-    torch.cuda._sleep(200_000)
+    # and not the host's launch call (device time, as the timing rules ask; `timing` in the line says so).  (0.1 ms was
+    # not enough on a box whose host needed 37 us per eager launch.)
+    torch.cuda._sleep(1_000_000)
     e0.record(stream)
     if graph is not None:
         graph.replay()
